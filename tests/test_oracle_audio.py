@@ -1,0 +1,147 @@
+"""
+Pins oracle/audio_np.py (the numpy restatement that travels to the GPU box) against
+ (1) golden vectors produced by the REFERENCE's own code (tests/golden/make_golden.py),
+ (2) scipy.signal.stft — the north_star's external 1e-5 criterion,
+ (3) hand-derived known answers.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import audio_np as A
+
+CASES = {
+    "audio_c1_sine":    (lambda: A.synth_sine(1.0),          60, 60.0, (15, 129)),
+    "audio_noise":      (lambda: A.synth_noise(1.0, seed=0), 60, 60.0, (15, 129)),
+    "audio_chirp_1000": (lambda: A.synth_chirp(1.5),         30, 24.0, None),
+    "audio_short":      (lambda: A.synth_noise(0.25, seed=3), 30, 60.0, (15, 129)),
+}
+
+
+def config_for(fps, notes) -> A.TrackConfig:
+    bank = A.BankConfig.from_notes(*notes, piano=True) if notes else A.BankConfig()
+    return A.TrackConfig(fps=fps, bank=bank)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_track_matches_reference_golden(name, golden_dir):
+    make, frames, fps, notes = CASES[name]
+    gold = np.load(golden_dir/f"{name}.npz")
+    x = make()
+    assert zlib.crc32(x.tobytes()) == int(gold["input_crc32"]), "synthetic input drifted"
+    cfg = config_for(fps, notes)
+    got = A.audio_track(x, frames, cfg, keep_magnitude=True)
+
+    # Host-side bookkeeping: exact
+    assert np.array_equal(got["tell"], gold["tell"])
+    assert np.array_equal(got["time"], gold["time"])
+    assert np.array_equal(got["dt"], gold["dt"])
+
+    # Filterbank: exact (same float64 → float32 arithmetic)
+    indptr, idx, val = A.filterbank_csr(A.filterbank_matrix(cfg.bank))
+    assert np.array_equal(indptr, gold["bank_indptr"])
+    assert np.array_equal(idx, gold["bank_indices"])
+    assert np.array_equal(val, gold["bank_data"])
+    assert np.array_equal(A.spectrogram_frequencies(cfg.bank), gold["bank_frequencies"])
+
+    # Numeric stages: the restatement runs the same numpy ops → bit-exact
+    assert np.array_equal(got["mag"][gold["mag_frames"]], gold["mag"])
+    for key in ("spec", "column", "vol_target", "std_target", "volume", "volume_integral", "std", "wave"):
+        assert np.array_equal(got[key], gold[key]), key
+
+
+def test_sine_known_answers(golden_dir):
+    """440 Hz → bin 54 of 115 (439.33 Hz), pre-bank peak ≈ (N/4)²"""
+    cfg = config_for(60.0, (15, 129))
+    assert cfg.bank.bins == 115
+    f = A.spectrogram_frequencies(cfg.bank)
+    assert abs(f[0] - 18.8919) < 1e-3 and abs(f[-1] - 14492.575) < 1e-2
+    got = A.audio_track(A.synth_sine(1.0), 60, cfg, keep_magnitude=True, waveform=False, scalars=False)
+    assert got["spec"][59].argmax(axis=1).tolist() == [54, 54]
+    assert abs(f[54] - 439.33) < 0.01
+    assert abs(got["mag"][59].max() / (4096/4)**2 - 1) < 0.05
+    # Frame 0 reads one sample and the newest sample is excluded → all-zero window
+    assert got["tell"][0] == 1 and not got["mag"][0].any()
+
+
+def test_frame_window_indices():
+    """App. A.1: window of frame k = clip samples [735k-4097, 735k-1), zero-filled"""
+    x = np.arange(1, 20001, dtype=np.float32)[None, :].repeat(2, 0)
+    w = A.last_n(x, 735*6, 4096)
+    assert w.shape == (2, 4096)
+    lo = 735*6 - 4097
+    assert w[0, 0] == x[0, lo] and w[0, -1] == x[0, 735*6 - 2]
+    w = A.last_n(x, 735*2, 4096)
+    assert not w[0, :4096 - (1470 - 1)].any() and w[0, -1] == x[0, 1468]
+
+
+def test_stft_identity_against_scipy():
+    """fft()[c] == (|Z|·Σw)² with scipy.signal.stft(window=np.hanning) — within 1e-5 of peak"""
+    import scipy.signal
+    x = A.synth_chirp(1.0)
+    n, hop, frames = 4096, 735, 40
+    cfg = config_for(60.0, (15, 129))
+    got = A.audio_track(x, frames, cfg, keep_magnitude=True, waveform=False, scalars=False)
+    padded = np.concatenate([np.zeros((2, n + 1), np.float32), x], axis=1)
+    w = np.hanning(n)
+    _, _, Z = scipy.signal.stft(padded.astype(np.float64), window=w, nperseg=n, noverlap=n - hop,
+        boundary=None, padded=False, detrend=False, scaling="spectrum", return_onesided=True)
+    # segment j starts at padded index hop*j == clip index hop*j - (n+1) → frame k=j (k≥1)
+    ref = (np.abs(Z)*w.sum())**2
+    for k in (1, 2, 7, 20, 39):
+        err = np.abs(got["mag"][k] - ref[:, :, k]).max()/ref[:, :, k].max()
+        assert err < 1e-5, (k, err)
+
+
+def test_dynamics_step_response_and_branches():
+    """Critically damped step response approaches the target without overshoot; dt=0 is a no-op;
+    f=10 at 60 fps takes the pole-matching branch (App. A.5)"""
+    d = A.Dynamics(frequency=4, zeta=1, response=0, value=np.zeros(3, np.float32))
+    assert d.next(np.ones(3, np.float32), dt=0.0) is d.value and not d.value.any()
+    ys = [float(d.next(np.ones(3, np.float32), dt=1/60)[0]) for _ in range(240)]
+    assert max(ys) <= 1.0 + 1e-4 and abs(ys[-1] - 1) < 1e-3 and d.value.dtype == np.float32
+    k1, k2 = A.Dynamics(frequency=4).coefficients(1/60)
+    assert abs(k1 - 0.0795775) < 1e-6 and abs(k2 - 1.5831e-3) < 1e-6
+    fast = A.Dynamics(frequency=10)
+    assert fast.radians/60 >= fast.zeta
+    k1, k2 = fast.coefficients(1/60)
+    t1 = np.exp(-fast.radians/60); t2 = (1/60)/(1 + t1*t1 - 2*t1)
+    assert abs(k1 - t2*(1 - t1*t1)) < 1e-12 and abs(k2 - t2/60) < 1e-12
+
+
+def test_filterbank_rows():
+    cfg = config_for(60.0, (15, 129))
+    m = A.filterbank_matrix(cfg.bank)
+    assert m.shape == (115, 2049) and (m != 0).sum() == 453
+    assert ((m != 0).sum(axis=1) <= 4).all() and ((m != 0).sum(axis=1) >= 3).all()
+    # Gaussian of area 1 sampled at unit spacing → rows sum to ≈1
+    assert np.abs(m.sum(axis=1) - 1).max() < 2e-3
+    d = A.filterbank_matrix(A.BankConfig())
+    assert d.shape == (1000, 2049) and (d != 0).sum() == 3934
+
+
+def test_notes():
+    assert A.note_from_frequency(440.0) == 69 and A.note_frequency(69) == 440.0
+    assert A.note_from_frequency(20) == 15 and A.note_from_frequency(14000) == 129
+    assert A.note_from_frequency(18000) == 133
+
+
+@pytest.mark.reference
+def test_restatement_against_live_reference():
+    """Same comparison as the golden test, but against the reference imported right now (build
+    container only) on an input that is not in the fixtures"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no /root/reference here")
+    R = ref_loader.load()
+    x = A.synth_noise(0.5, seed=11)*np.linspace(0, 1, 22050, dtype=np.float32)
+    cfg = A.TrackConfig(bank=A.BankConfig.from_notes(15, 133, piano=True))
+    got = A.audio_track(x, 20, cfg, keep_magnitude=True)
+    audio = R.BrokenAudio(); spec = R.BrokenSpectrogram(audio=audio)
+    spec.from_notes(start=15, end=133, piano=True)
+    prev = 0
+    for k in range(20):
+        audio.add_data(x[:, prev:got["tell"][k]]); prev = got["tell"][k]
+        assert np.array_equal(spec.fft(), got["mag"][k])
+        assert np.array_equal(spec.next(), got["spec"][k])
