@@ -1,0 +1,234 @@
+/*
+ * sfb200.h — C ABI of libsfb200.so, the B200-native backend of ShaderFlow's offline render hot loop.
+ *
+ * The reference (BrokenSource/ShaderFlow v0.11.3) has no FFI of its own: its native back-ends are
+ * third-party wheels reached through Python objects (moderngl, numpy.fft, scipy.sparse, turbopipe).
+ * Every entry point below names the reference call site(s) it replaces (paths relative to the reference
+ * root). The binding a maintainer adds on the reference side is a ctypes stub: see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SFB_E* code; sfb_last_error() gives the
+ *     thread-local message (reference convention: Python exceptions — the ctypes wrapper raises
+ *     RuntimeError, mirroring shader.py:354-355 / exporting.py:157-162 / texture.py:251-252);
+ *   - one sfb_ctx per (process, device); all calls for a ctx come from one host thread; work is enqueued
+ *     on the ctx stream and is asynchronous unless stated (the GL context had the same rule);
+ *   - pointers named *_dev are device pointers (e.g. torch tensor.data_ptr()), *_host are host pointers;
+ *   - images are bottom-row-first like GL framebuffers / fbo.read_into (exporting.py:165-174);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with SFB_ECUDA.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_VERSION 100  /* 0.1.0 */
+
+enum {
+    SFB_OK = 0,
+    SFB_EINVAL = -1,     /* bad argument */
+    SFB_ECUDA = -2,      /* CUDA runtime / driver error, or no device */
+    SFB_ENOTFOUND = -3,  /* unknown scene / fragment hash */
+    SFB_ENOMEM = -4,
+    SFB_EIO = -5,        /* sink write failed */
+    SFB_ESTATE = -6,     /* call made in the wrong state */
+};
+
+typedef struct sfb_ctx sfb_ctx;
+typedef struct sfb_tex sfb_tex;
+typedef struct sfb_pipe sfb_pipe;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Library / context — replaces scene.py:143-157 (window + moderngl.Context creation) and
+ * scene.py:100-107 (teardown). `stream` is a cudaStream_t (0 = legacy default stream); pass
+ * torch.cuda.current_stream().cuda_stream so torch events bracket the work. */
+int         sfb_version(void);
+const char* sfb_last_error(void);
+int         sfb_device_count(int* count);
+int         sfb_ctx_create(int device, void* stream, sfb_ctx** out);
+int         sfb_ctx_destroy(sfb_ctx* ctx);
+int         sfb_ctx_set_stream(sfb_ctx* ctx, void* stream);
+int         sfb_sync(sfb_ctx* ctx);                       /* blocks: cudaStreamSynchronize */
+/* Kernel launches issued through this ctx since creation (bench.py's `gpu_launches`) */
+int         sfb_launch_count(sfb_ctx* ctx, uint64_t* count);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Host-side time base (no GPU). Replaces the freewheel SchedulerTask (scheduler.py:86-89,134-173) +
+ * ShaderScene.next's time integration (scene.py:476-479) + BrokenAudioReader.stream's chunk rule
+ * (ffmpeg.py:1306-1330). For frame k writes the values modules see DURING that frame:
+ *   time[k], dt[k]  — scene.time / scene.dt;   tell[k] — samples consumed after ShaderAudio.update.
+ * total_samples < 0 means an endless stream. Any output pointer may be NULL. */
+int sfb_frame_clock(int n_frames, double fps, double speed, int samplerate, int channels,
+                    int64_t total_samples, double* time_host, double* dt_host, int64_t* tell_host);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Audio: STFT → filterbank spectrogram (kernel K1).
+ * Replaces, for a batch of frames at once, BrokenSpectrogram.fft + .next (audio/spectrogram.py:155-176):
+ * numpy.fft.rfft (pocketfft, float64) and scipy.sparse.csr_matrix.dot, plus the ring slicing of
+ * BrokenAudio.get_last_n_samples (audio/module.py:137-138).
+ *
+ *   pcm_dev      [channels][n_samples] float32 planar — the whole clip resident in HBM
+ *   tell_dev     [n_frames] int64 — samples consumed at each frame (sfb_frame_clock); the window of frame
+ *                k is clip samples [tell-N-1, tell-1), zero where negative (newest sample excluded)
+ *   fft_n        N = 2^fft_n, 8 <= fft_n <= 13; channels must be 1 or 2
+ *   window_kind  SFB_WINDOW_*   (spectrogram.py:90-108)      magnitude_kind SFB_MAGNITUDE_* (:20-26)
+ *   csr_*        filterbank (bins x (N/2+1)) in CSR, float32 (spectrogram.py:194-224), device pointers
+ *   volume_kind  SFB_VOLUME_* epilogue (:28-41; the reference never applies it — LINEAR = parity)
+ *   mag_out_dev  optional [n_frames][channels][N/2+1] float32 (NULL to skip)
+ *   spec_out_dev [n_frames][bins][channels] float32 — texel b of frame k = (L_b, R_b), the layout
+ *                ShaderSpectrogram writes to its RG32F texture column (spectrogram.py:306-311)
+ */
+enum { SFB_WINDOW_HANNING = 0, SFB_WINDOW_HANN_POISSON = 1, SFB_WINDOW_NONE = 2 };
+enum { SFB_MAGNITUDE_POWER = 0, SFB_MAGNITUDE_AMPLITUDE = 1 };
+enum { SFB_VOLUME_LINEAR = 0, SFB_VOLUME_SQRT = 1, SFB_VOLUME_DBFS = 2, SFB_VOLUME_DBFS_TREMX = 3 };
+
+int sfb_stft_mel(sfb_ctx* ctx, const float* pcm_dev, int64_t n_samples, int channels, int fft_n,
+                 const int64_t* tell_dev, int n_frames, int window_kind, int magnitude_kind,
+                 const int32_t* csr_indptr_dev, const int32_t* csr_indices_dev, const float* csr_data_dev,
+                 int bins, int volume_kind, float* mag_out_dev, float* spec_out_dev);
+
+/* Audio: everything else the audio modules compute per frame (kernel K2), for a batch of frames.
+ *   (1) second-order dynamics over the spectrogram columns — DynamicNumber.next (dynamics.py:197-250)
+ *       as ShaderSpectrogram.update drives it (spectrogram.py:303-311): float32 state, in place on
+ *       spec_inout_dev [n_frames][bins][channels]; a recurrence over frames, run as one sequential scan;
+ *   (2) volume / std targets over the last 0.1 s (audio/module.py:457-458) and their two ShaderDynamics
+ *       (audio/module.py:413-421; float64 state): scalars_out_dev [n_frames][SFB_SCALARS] float64 =
+ *       {volume, volume_integral, std, volume_target, std_target};
+ *   (3) waveform reducer rows (audio/waveform.py:14-22,64-87): wave_out_dev [n_frames][points][channels].
+ * dt_dev [n_frames] float64 is scene.dt per frame (sfb_frame_clock). Any of spec_inout_dev /
+ * scalars_out_dev / wave_out_dev may be NULL to skip that part.
+ */
+enum { SFB_SCALAR_VOLUME = 0, SFB_SCALAR_VOLUME_INTEGRAL = 1, SFB_SCALAR_STD = 2,
+       SFB_SCALAR_VOLUME_TARGET = 3, SFB_SCALAR_STD_TARGET = 4, SFB_SCALARS = 5 };
+enum { SFB_REDUCER_AVERAGE = 0, SFB_REDUCER_RMS = 1, SFB_REDUCER_STD = 2 };
+
+typedef struct sfb_dynamics_params {   /* dynamics.py:140-158 */
+    double frequency, zeta, response, precision;
+} sfb_dynamics_params;
+
+int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_samples, int channels, int samplerate,
+                    const int64_t* tell_dev, const double* dt_dev, int n_frames,
+                    float* spec_inout_dev, int bins, const sfb_dynamics_params* spec_dynamics,
+                    double* scalars_out_dev,
+                    float* wave_out_dev, int wave_points, int wave_chunk, int wave_reducer);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Textures — replaces moderngl Context.texture / Texture.write / .filter / .repeat_x/y as used by
+ * ShaderTexture.make/apply/write (texture.py:250-283,313-325). Backed by a cudaArray + texture object
+ * (hardware filtering) and a pitch-linear mirror (exact float32 filtering, TMA staging).
+ * components 1..4 (3 is stored padded to 4, alpha reads 1 like GL); rows bottom-first. */
+enum { SFB_DTYPE_U8 = 0, SFB_DTYPE_F32 = 1, SFB_DTYPE_F16 = 2 };
+enum { SFB_FILTER_NEAREST = 0, SFB_FILTER_LINEAR = 1 };
+
+int sfb_tex_create(sfb_ctx* ctx, int width, int height, int components, int dtype,
+                   int filter, int repeat_x, int repeat_y, sfb_tex** out);
+int sfb_tex_destroy(sfb_tex* tex);
+int sfb_tex_set_sampling(sfb_tex* tex, int filter, int repeat_x, int repeat_y);
+/* data: tightly packed w*h*components elements of the texture dtype; on_device selects the pointer kind */
+int sfb_tex_write(sfb_tex* tex, const void* data, int on_device, int x, int y, int w, int h);
+/* Zero-copy: sample straight from a device buffer laid out [height][width][components_padded] of the
+ * texture dtype (e.g. a row of sfb_stft_mel's output) — the GL upload of texture.py:321 disappears.
+ * Pass NULL to go back to the texture's own storage. */
+int sfb_tex_bind_external(sfb_tex* tex, const void* data_dev);
+int sfb_tex_read(sfb_tex* tex, void* data_host);          /* blocks; debugging / tests */
+/* texture(sampler, uv) probe: n normalised coordinates uv_dev [n][2] → out_dev [n][4] float32, with the
+ * texture's filter / wrap state and SFB_FILTER_EXACT or SFB_FILTER_HARDWARE (parity tests of the sampler) */
+int sfb_tex_sample(sfb_tex* tex, const float* uv_dev, int n, int flags, float* out_dev);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Programs — replaces ShaderProgram.compile/use_pipeline/render (shader.py:313-405): the GLSL of the
+ * in-scope scenes is transliterated ahead of time to CUDA device functions; "compile" is a lookup. */
+enum {
+    SFB_SCENE_DEFAULT = 0,     /* resources/shaders/fragment/default.glsl      (Basic)      */
+    SFB_SCENE_SHADERTOY = 1,   /* examples/basic/shaders/shadertoy.frag        (ShaderToy)  */
+    SFB_SCENE_VISUALIZER = 2,  /* examples/basic/shaders/visualizer.frag       (Visualizer) */
+    SFB_SCENE_BARS = 3,        /* examples/basic/shaders/bars.frag             (MusicBars)  */
+    SFB_SCENE_WAVEFORM = 4,    /* examples/basic/shaders/waveform.frag         (Waveform)   */
+    SFB_SCENE_MANDELBROT = 5,  /* examples/fractals/shaders/mandelbrot.frag    (Mandelbrot) */
+    SFB_SCENE_TETRATION = 6,   /* examples/fractals/shaders/tetration.frag     (Tetration)  */
+    SFB_SCENE_RAYMARCH = 7,    /* examples/basic/shaders/raymarch.frag         (RayMarch)   */
+    SFB_SCENE_COUNT = 8,
+};
+
+#define SFB_MAX_EXTRA 16
+#define SFB_MAX_SAMPLERS 8
+
+/* One POD block passed by value to the kernel (__grid_constant__): the uniforms of
+ * ShaderScene.pipeline (scene.py:687-703), ShaderCamera.pipeline + its ShaderDynamics (camera.py:146-201),
+ * then `extra` slots for module / user uniforms in the order sfb_scene_info reports. Values are the
+ * float32 casts GL would make at upload. */
+typedef struct sfb_uniforms {
+    float iTime, iTau, iDuration, iDeltatime;
+    float iResolution[2];
+    float iWantAspect, iQuality, iSSAA, iFramerate;
+    int32_t iFrame, iRealtime, iLayer, iMouseInside;
+    float iMouse[2];
+    int32_t iMouse1, iMouse2;
+    int32_t iCameraMode, iCameraProjection;
+    float iCameraPosition[3], iCameraRight[3], iCameraUpward[3], iCameraForward[3], iCameraZenith[3];
+    float iCameraZoom, iCameraIsometric, iCameraFocalLength, iCameraOrbital, iCameraDolly, iCameraSeparation;
+    float extra[SFB_MAX_EXTRA][4];
+} sfb_uniforms;
+
+typedef struct sfb_scene_info {
+    const char* name;                       /* "visualizer", ... */
+    const char* reference;                  /* reference file the kernel transliterates */
+    int n_extra;    const char* extra[SFB_MAX_EXTRA];       /* uniform names → extra[i] slots */
+    int n_samplers; const char* samplers[SFB_MAX_SAMPLERS]; /* sampler2D names → samplers[i] */
+} sfb_scene_info;
+
+int sfb_scene_lookup(const char* name, int* scene);       /* SFB_ENOTFOUND when not built in */
+int sfb_scene_info_get(int scene, sfb_scene_info* info);
+
+/* Render flags */
+enum {
+    SFB_FILTER_EXACT = 0,      /* float32 bilinear on point-fetched texels (parity default)           */
+    SFB_FILTER_HARDWARE = 1,   /* cudaTextureObject filtering (9-bit weights, like GL hardware)       */
+};
+
+/* iScreen pass (K3): one thread per fragment of a target_w x target_h RGBA8 target — replaces
+ * ShaderProgram.render_to_fbo's fullscreen TRIANGLE_STRIP draw (shader.py:367-375,398-403).
+ * dst_rgba8_dev: target_w*target_h*4 bytes. dst_f32_dev: optional float4 per fragment, the colour
+ * BEFORE the 8-bit store (parity tests); NULL normally. */
+int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                      sfb_tex* const* samplers, int n_samplers, int flags,
+                      int target_w, int target_h, void* dst_rgba8_dev, float* dst_f32_dev);
+
+/* Final pass (K4): fragment/final.glsl:3-33 over an RGBA8 iScreen (LINEAR, CLAMP_TO_EDGE) into a
+ * width x height target with `components` 3 (rgb24, what ffmpeg gets: exporting.py:94-103) or 4. */
+int sfb_render_final(sfb_ctx* ctx, const void* screen_rgba8_dev, int screen_w, int screen_h,
+                     int width, int height, int subsample, int components, void* dst_dev);
+
+/* Fused K3+K4: shades the ssaa x ssaa sub-samples of each output pixel, quantises each to 8 bit
+ * exactly like the RGBA8 iScreen store, box-averages and quantises again. Bit-identical to
+ * screen+final whenever final.glsl degenerates to a box filter: integer ssaa with
+ * subsample == ssaa or 2*subsample == ssaa; other combinations → SFB_EINVAL.
+ * The iScreen texture never touches HBM. */
+int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                     sfb_tex* const* samplers, int n_samplers, int flags,
+                     int width, int height, int ssaa, int subsample, int components, void* dst_dev);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Frame sink — replaces turbopipe.pipe/sync/done + fbo.read_into (exporting.py:140-174): a ring of
+ * n_buffers device frames, each paired with a pinned host buffer; submit enqueues an async D2H on a copy
+ * stream ordered after the render stream, a writer thread does write(fd) in submission order.
+ * fd < 0 is a null sink (frames are copied to the host and dropped).
+ *   acquire: device pointer of the next ring frame to render into; blocks while its previous contents
+ *            are still being copied / written (the back-pressure of exporting.py:168's turbopipe.sync).
+ *   submit:  frame_dev NULL or the acquired pointer → zero-copy; any other device pointer is first
+ *            copied D2D into the ring frame on the render stream. */
+int sfb_pipe_open(sfb_ctx* ctx, int fd, int n_buffers, size_t frame_bytes, sfb_pipe** out);
+int sfb_pipe_acquire(sfb_pipe* pipe, void** frame_dev);
+int sfb_pipe_submit(sfb_pipe* pipe, const void* frame_dev);
+int sfb_pipe_sync(sfb_pipe* pipe);                       /* blocks until every submitted frame is written */
+int sfb_pipe_stats(sfb_pipe* pipe, uint64_t* frames, uint64_t* bytes);
+int sfb_pipe_close(sfb_pipe* pipe);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */

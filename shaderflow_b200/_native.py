@@ -1,0 +1,330 @@
+"""
+ctypes binding of libsfb200.so (include/sfb200.h) — the only door between the Python host and the
+CUDA backend. PyTorch tensors are used purely as device buffers: every wrapper takes `tensor.data_ptr()`.
+
+There is no CPU fallback: `lib()` raises if the library is missing, `Context()` raises without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from pathlib import Path
+
+LIBRARY = Path(__file__).resolve().parent/"libsfb200.so"
+
+MAX_EXTRA, MAX_SAMPLERS = 16, 8
+OK, EINVAL, ECUDA, ENOTFOUND, ENOMEM, EIO, ESTATE = 0, -1, -2, -3, -4, -5, -6
+WINDOW = dict(hanning=0, hann_poisson=1, none=2)
+MAGNITUDE = dict(power=0, amplitude=1)
+VOLUME = dict(linear=0, sqrt=1, dbfs=2, dbfs_tremx=3)
+REDUCER = dict(average=0, rms=1, std=2)
+DTYPE_U8, DTYPE_F32, DTYPE_F16 = 0, 1, 2
+FILTER_NEAREST, FILTER_LINEAR = 0, 1
+FILTER_EXACT, FILTER_HARDWARE = 0, 1
+SCALARS = 5
+SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
+
+
+class Uniforms(C.Structure):
+    """struct sfb_uniforms"""
+    _fields_ = [
+        ("iTime", c_float), ("iTau", c_float), ("iDuration", c_float), ("iDeltatime", c_float),
+        ("iResolution", c_float*2),
+        ("iWantAspect", c_float), ("iQuality", c_float), ("iSSAA", c_float), ("iFramerate", c_float),
+        ("iFrame", c_int32), ("iRealtime", c_int32), ("iLayer", c_int32), ("iMouseInside", c_int32),
+        ("iMouse", c_float*2),
+        ("iMouse1", c_int32), ("iMouse2", c_int32),
+        ("iCameraMode", c_int32), ("iCameraProjection", c_int32),
+        ("iCameraPosition", c_float*3), ("iCameraRight", c_float*3), ("iCameraUpward", c_float*3),
+        ("iCameraForward", c_float*3), ("iCameraZenith", c_float*3),
+        ("iCameraZoom", c_float), ("iCameraIsometric", c_float), ("iCameraFocalLength", c_float),
+        ("iCameraOrbital", c_float), ("iCameraDolly", c_float), ("iCameraSeparation", c_float),
+        ("extra", (c_float*4)*MAX_EXTRA),
+    ]
+
+    @classmethod
+    def defaults(cls, width: int = 1920, height: int = 1080) -> "Uniforms":
+        """A freshly built scene in an export (scene.py:687-703, camera.py:146-201)"""
+        u = cls()
+        u.iDuration, u.iResolution[:] = 10.0, (width, height)
+        u.iWantAspect, u.iQuality, u.iSSAA, u.iFramerate = width/height, 0.5, 1.0, 60.0
+        u.iCameraMode = 1
+        u.iCameraRight[:], u.iCameraUpward[:], u.iCameraForward[:] = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+        u.iCameraZenith[:] = (0, 1, 0)
+        u.iCameraZoom, u.iCameraFocalLength, u.iCameraSeparation = 1.0, 1.0, 0.05
+        return u
+
+
+class DynamicsParams(C.Structure):
+    _fields_ = [("frequency", c_double), ("zeta", c_double), ("response", c_double), ("precision", c_double)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [
+        ("name", c_char_p), ("reference", c_char_p),
+        ("n_extra", c_int), ("extra", c_char_p*MAX_EXTRA),
+        ("n_samplers", c_int), ("samplers", c_char_p*MAX_SAMPLERS),
+    ]
+
+
+_PROTOTYPES = dict(
+    sfb_version=(c_int, []),
+    sfb_last_error=(c_char_p, []),
+    sfb_device_count=(c_int, [POINTER(c_int)]),
+    sfb_ctx_create=(c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    sfb_ctx_destroy=(c_int, [c_void_p]),
+    sfb_ctx_set_stream=(c_int, [c_void_p, c_void_p]),
+    sfb_sync=(c_int, [c_void_p]),
+    sfb_launch_count=(c_int, [c_void_p, POINTER(c_uint64)]),
+    sfb_frame_clock=(c_int, [c_int, c_double, c_double, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    sfb_stft_mel=(c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    sfb_audio_track=(c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
+                             c_void_p, c_int, POINTER(DynamicsParams), c_void_p, c_void_p, c_int, c_int, c_int]),
+    sfb_tex_create=(c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    sfb_tex_destroy=(c_int, [c_void_p]),
+    sfb_tex_set_sampling=(c_int, [c_void_p, c_int, c_int, c_int]),
+    sfb_tex_write=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    sfb_tex_bind_external=(c_int, [c_void_p, c_void_p]),
+    sfb_tex_read=(c_int, [c_void_p, c_void_p]),
+    sfb_tex_sample=(c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    sfb_scene_lookup=(c_int, [c_char_p, POINTER(c_int)]),
+    sfb_scene_info_get=(c_int, [c_int, POINTER(SceneInfo)]),
+    sfb_render_screen=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
+                               c_int, c_int, c_void_p, c_void_p]),
+    sfb_render_final=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    sfb_render_frame=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
+                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    sfb_pipe_open=(c_int, [c_void_p, c_int, c_int, c_size_t, POINTER(c_void_p)]),
+    sfb_pipe_acquire=(c_int, [c_void_p, POINTER(c_void_p)]),
+    sfb_pipe_submit=(c_int, [c_void_p, c_void_p]),
+    sfb_pipe_sync=(c_int, [c_void_p]),
+    sfb_pipe_stats=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
+    sfb_pipe_close=(c_int, [c_void_p]),
+)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libsfb200.so once and types every export of include/sfb200.h"""
+    global _lib
+    if _lib is None:
+        if not LIBRARY.exists():
+            raise RuntimeError(
+                f"{LIBRARY} is missing. Build it with `python -m shaderflow_b200.build` "
+                "(needs nvcc); shaderflow_b200 has no CPU fallback.")
+        handle = C.CDLL(str(LIBRARY))
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)      # AttributeError here = header and library disagree
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+def exported_symbols() -> list[str]:
+    return list(_PROTOTYPES)
+
+
+def check(code: int) -> None:
+    if code != OK:
+        message = lib().sfb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libsfb200: {message} (code {code})")
+
+
+def _ptr(obj) -> c_void_p | None:
+    """tensor / ndarray / int / None → void*"""
+    if obj is None:
+        return None
+    if isinstance(obj, int):
+        return c_void_p(obj)
+    if hasattr(obj, "data_ptr"):
+        return c_void_p(obj.data_ptr())
+    if hasattr(obj, "ctypes"):
+        return c_void_p(obj.ctypes.data)
+    raise TypeError(f"cannot take the address of {type(obj).__name__}")
+
+
+def device_count() -> int:
+    n = c_int(0)
+    code = lib().sfb_device_count(byref(n))
+    return n.value if code == OK else 0
+
+
+def frame_clock(n_frames: int, fps: float = 60.0, speed: float = 1.0, samplerate: int = 44100,
+                channels: int = 2, total_samples: int = -1):
+    """→ (time[f64], dt[f64], tell[i64]) numpy arrays; host only (sfb_frame_clock)"""
+    import numpy as np
+    time, dt, tell = np.zeros(n_frames), np.zeros(n_frames), np.zeros(n_frames, np.int64)
+    check(lib().sfb_frame_clock(n_frames, fps, speed, samplerate, channels, total_samples,
+                                _ptr(time), _ptr(dt), _ptr(tell)))
+    return time, dt, tell
+
+
+def scene_lookup(name: str) -> int:
+    scene = c_int(-1)
+    check(lib().sfb_scene_lookup(name.encode(), byref(scene)))
+    return scene.value
+
+
+def scene_info(scene: int) -> dict:
+    info = SceneInfo()
+    check(lib().sfb_scene_info_get(scene, byref(info)))
+    return dict(
+        name=info.name.decode(), reference=info.reference.decode(),
+        extra=[info.extra[i].decode() for i in range(info.n_extra)],
+        samplers=[info.samplers[i].decode() for i in range(info.n_samplers)],
+    )
+
+
+class Texture:
+    """sfb_tex handle"""
+    def __init__(self, ctx: "Context", width: int, height: int, components: int, dtype: int,
+                 linear: bool = True, repeat_x: bool = True, repeat_y: bool = True):
+        self.ctx, self.handle = ctx, c_void_p()
+        self.width, self.height, self.components, self.dtype = width, height, components, dtype
+        check(lib().sfb_tex_create(ctx.handle, width, height, components, dtype,
+                                   FILTER_LINEAR if linear else FILTER_NEAREST, int(repeat_x), int(repeat_y), byref(self.handle)))
+
+    def set_sampling(self, linear: bool, repeat_x: bool, repeat_y: bool) -> None:
+        check(lib().sfb_tex_set_sampling(self.handle, FILTER_LINEAR if linear else FILTER_NEAREST, int(repeat_x), int(repeat_y)))
+
+    def write(self, data, viewport: tuple[int, int, int, int] | None = None) -> None:
+        """data: numpy array / bytes (host) or a CUDA tensor (device), tightly packed"""
+        x, y, w, h = viewport or (0, 0, self.width, self.height)
+        on_device = bool(getattr(data, "is_cuda", False))
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            keep = (C.c_char*len(data)).from_buffer_copy(data)
+            check(lib().sfb_tex_write(self.handle, C.cast(keep, c_void_p), 0, x, y, w, h))
+            return
+        check(lib().sfb_tex_write(self.handle, _ptr(data), int(on_device), x, y, w, h))
+
+    def bind_external(self, pointer) -> None:
+        check(lib().sfb_tex_bind_external(self.handle, _ptr(pointer)))
+
+    def read(self):
+        import numpy as np
+        padded = 4 if self.components == 3 else self.components
+        dt = {DTYPE_U8: np.uint8, DTYPE_F32: np.float32, DTYPE_F16: np.float16}[self.dtype]
+        out = np.empty((self.height, self.width, padded), dt)
+        check(lib().sfb_tex_read(self.handle, _ptr(out)))
+        return out
+
+    def sample(self, uv, out, flags: int = FILTER_EXACT) -> None:
+        """uv (n, 2) f32 cuda → out (n, 4) f32 cuda"""
+        check(lib().sfb_tex_sample(self.handle, _ptr(uv), uv.shape[0], flags, _ptr(out)))
+
+    def destroy(self) -> None:
+        if self.handle:
+            lib().sfb_tex_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try: self.destroy()
+        except Exception: pass
+
+
+class Pipe:
+    """sfb_pipe handle: device ring + pinned ring + writer thread"""
+    def __init__(self, ctx: "Context", fd: int, buffers: int, frame_bytes: int):
+        self.ctx, self.handle, self.frame_bytes = ctx, c_void_p(), frame_bytes
+        check(lib().sfb_pipe_open(ctx.handle, fd, buffers, frame_bytes, byref(self.handle)))
+
+    def acquire(self) -> int:
+        p = c_void_p()
+        check(lib().sfb_pipe_acquire(self.handle, byref(p)))
+        return p.value
+
+    def submit(self, frame=None) -> None:
+        check(lib().sfb_pipe_submit(self.handle, _ptr(frame)))
+
+    def sync(self) -> None:
+        check(lib().sfb_pipe_sync(self.handle))
+
+    def stats(self) -> tuple[int, int]:
+        f, b = c_uint64(), c_uint64()
+        check(lib().sfb_pipe_stats(self.handle, byref(f), byref(b)))
+        return f.value, b.value
+
+    def close(self) -> None:
+        if self.handle:
+            handle, self.handle = self.handle, c_void_p()
+            check(lib().sfb_pipe_close(handle))
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
+class Context:
+    """sfb_ctx handle. `stream` defaults to torch's current stream on `device`"""
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.handle = c_void_p()
+        self.device = device
+        if stream is None:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError("shaderflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            torch.cuda.set_device(device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib().sfb_ctx_create(device, c_void_p(stream), byref(self.handle)))
+
+    def set_stream(self, stream: int) -> None:
+        check(lib().sfb_ctx_set_stream(self.handle, c_void_p(stream)))
+
+    def sync(self) -> None:
+        check(lib().sfb_sync(self.handle))
+
+    @property
+    def launches(self) -> int:
+        n = c_uint64()
+        check(lib().sfb_launch_count(self.handle, byref(n)))
+        return n.value
+
+    # -- audio ------------------------------------------------------------------------------ #
+
+    def stft_mel(self, pcm, tell, fft_n: int, csr=None, *, window: int = 0, magnitude: int = 0,
+                 volume: int = 0, mag_out=None, spec_out=None) -> None:
+        """pcm (ch, n) f32 cuda; tell (F,) i64 cuda; csr = (indptr, indices, data, bins) cuda tensors"""
+        channels, n = pcm.shape
+        indptr, indices, data, bins = csr if csr is not None else (None, None, None, 0)
+        check(lib().sfb_stft_mel(self.handle, _ptr(pcm), n, channels, fft_n, _ptr(tell), tell.shape[0],
+            window, magnitude, _ptr(indptr), _ptr(indices), _ptr(data), bins, volume, _ptr(mag_out), _ptr(spec_out)))
+
+    def audio_track(self, pcm, samplerate: int, tell, dt, *, spec=None, bins: int = 0,
+                    dynamics: tuple[float, float, float, float] = (4.0, 1.0, 0.0, 1e-6),
+                    scalars=None, wave=None, wave_points: int = 180, wave_chunk: int = 735, wave_reducer: int = 0) -> None:
+        channels, n = pcm.shape
+        prm = DynamicsParams(*dynamics)
+        check(lib().sfb_audio_track(self.handle, _ptr(pcm), n, channels, samplerate, _ptr(tell), _ptr(dt), tell.shape[0],
+            _ptr(spec), bins, byref(prm), _ptr(scalars), _ptr(wave), wave_points, wave_chunk, wave_reducer))
+
+    # -- render ----------------------------------------------------------------------------- #
+
+    @staticmethod
+    def _samplers(textures):
+        arr = (c_void_p*max(1, len(textures)))(*[t.handle for t in textures])
+        return arr, len(textures)
+
+    def render_screen(self, scene: int, uniforms: Uniforms, textures, width: int, height: int, dst,
+                      dst_f32=None, flags: int = FILTER_EXACT) -> None:
+        arr, n = self._samplers(textures)
+        check(lib().sfb_render_screen(self.handle, scene, byref(uniforms), arr, n, flags, width, height, _ptr(dst), _ptr(dst_f32)))
+
+    def render_final(self, screen, screen_w: int, screen_h: int, width: int, height: int,
+                     subsample: int, components: int, dst) -> None:
+        check(lib().sfb_render_final(self.handle, _ptr(screen), screen_w, screen_h, width, height, subsample, components, _ptr(dst)))
+
+    def render_frame(self, scene: int, uniforms: Uniforms, textures, width: int, height: int,
+                     ssaa: int, subsample: int, components: int, dst, flags: int = FILTER_EXACT) -> None:
+        arr, n = self._samplers(textures)
+        check(lib().sfb_render_frame(self.handle, scene, byref(uniforms), arr, n, flags, width, height, ssaa, subsample, components, _ptr(dst)))
+
+    def destroy(self) -> None:
+        if self.handle:
+            lib().sfb_ctx_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try: self.destroy()
+        except Exception: pass

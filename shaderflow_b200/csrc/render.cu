@@ -1,0 +1,274 @@
+// render.cu — kernels K3 (iScreen pass), K4 (final.glsl) and the fused K3+K4, plus their C ABI.
+// Reference call sites replaced: shader.py:367-405 (render / render_to_fbo), scene.py:185-194
+// (iFinal / iScreen programs), resources/shaders/fragment/final.glsl.
+#include "scenes.cuh"
+
+using namespace glsl;
+
+// Colour store to an 8-bit attachment: clamp to [0,1] (NaN → 0), round half to even
+SFB_DEV unsigned int to_unorm8(float c) { return (unsigned int)__float2int_rn(__saturatef(c)*255.0f); }
+
+// ------------------------------------------------------------------------------------------------
+// K3: one thread per fragment of the Wr×Hr RGBA8 target
+
+template <int SCENE, bool HW>
+__global__ void __launch_bounds__(256) screen_kernel(const __grid_constant__ RenderParams P) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    const int j = blockIdx.y*blockDim.y + threadIdx.y;
+    if (i >= P.Wr || j >= P.Hr) return;
+    const Frag f = make_frag(P, i, j);
+    const vec4 c = shade<SCENE, HW>(P, f);
+    const size_t idx = size_t(j)*size_t(P.Wr) + size_t(i);
+    reinterpret_cast<uchar4*>(P.dst)[idx] =
+        make_uchar4(to_unorm8(c.x), to_unorm8(c.y), to_unorm8(c.z), to_unorm8(c.w));
+    if (P.dst_f32) reinterpret_cast<float4*>(P.dst_f32)[idx] = make_float4(c.x, c.y, c.z, c.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused K3+K4: one thread per OUTPUT pixel, ssaa×ssaa shaded sub-samples, each quantised to 8 bit
+// as the RGBA8 iScreen store would, integer box sum, one more 8-bit store. Tile = 32×8 pixels;
+// rgb24 rows are staged in shared memory and leave as 32-bit words.
+
+constexpr int TILE_X = 32, TILE_Y = 8;
+
+template <int SCENE, bool HW>
+__global__ void __launch_bounds__(TILE_X*TILE_Y) frame_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ unsigned int stage[TILE_Y][TILE_X];     // rgb24: first 24 words of each row are used
+    const int x = blockIdx.x*TILE_X + threadIdx.x;
+    const int y = blockIdx.y*TILE_Y + threadIdx.y;
+    const bool inside = (x < P.W) && (y < P.H);
+    const int S = P.ssaa;
+    unsigned int r = 0, g = 0, b = 0;
+    if (inside) {
+        for (int sy = 0; sy < S; sy++) {
+            for (int sx = 0; sx < S; sx++) {
+                const Frag f = make_frag(P, x*S + sx, y*S + sy);
+                const vec4 c = shade<SCENE, HW>(P, f);
+                r += to_unorm8(c.x); g += to_unorm8(c.y); b += to_unorm8(c.z);
+            }
+        }
+        // mean of S² bytes, then the RGB8 store of iFinal: round(mean) half-to-even
+        const float inv = 1.0f/float(S*S);
+        r = (unsigned int)__float2int_rn(float(r)*inv);
+        g = (unsigned int)__float2int_rn(float(g)*inv);
+        b = (unsigned int)__float2int_rn(float(b)*inv);
+    }
+    if (P.comps == 4) {
+        if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r, g, b, 255);
+        return;
+    }
+    const bool words = (P.W % 4 == 0) && (blockIdx.x*TILE_X + TILE_X <= P.W);
+    if (!words) {
+        if (inside) {
+            unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3;
+            p[0] = r; p[1] = g; p[2] = b;
+        }
+        return;
+    }
+    unsigned char* row = reinterpret_cast<unsigned char*>(stage[threadIdx.y]);
+    row[threadIdx.x*3 + 0] = r; row[threadIdx.x*3 + 1] = g; row[threadIdx.x*3 + 2] = b;
+    __syncwarp();
+    if (threadIdx.x < (TILE_X*3)/4 && y < P.H) {
+        unsigned int* out = reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(blockIdx.x*TILE_X))*3);
+        out[threadIdx.x] = stage[threadIdx.y][threadIdx.x];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: fragment/final.glsl:3-33 over an RGBA8 iScreen, LINEAR + CLAMP_TO_EDGE (scene.py:192-193)
+
+struct FinalParams {
+    const unsigned char* screen; int Ws, Hs;
+    int W, H, subsample, comps;
+    unsigned char* dst;
+};
+
+SFB_DEV vec3 screen_bilinear(const FinalParams& P, vec2 uv) {
+    float ub = uv.x*float(P.Ws) - 0.5f, vb = uv.y*float(P.Hs) - 0.5f;
+    float fx = floorf(ub), fy = floorf(vb);
+    float a = ub - fx, b = vb - fy;
+    int i0 = int(fx), j0 = int(fy);
+    auto fetch = [&](int i, int j) {
+        i = min(max(i, 0), P.Ws - 1); j = min(max(j, 0), P.Hs - 1);
+        uchar4 c = __ldg(reinterpret_cast<const uchar4*>(P.screen) + size_t(j)*size_t(P.Ws) + size_t(i));
+        return mk3(c.x/255.0f, c.y/255.0f, c.z/255.0f);
+    };
+    vec3 top = fetch(i0, j0)*(1.0f - a) + fetch(i0 + 1, j0)*a;
+    vec3 bot = fetch(i0, j0 + 1)*(1.0f - a) + fetch(i0 + 1, j0 + 1)*a;
+    return top*(1.0f - b) + bot*b;
+}
+
+__global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ FinalParams P) {
+    const int x = blockIdx.x*blockDim.x + threadIdx.x;
+    const int y = blockIdx.y*blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H) return;
+    // astuv of the W×H final target (same rasteriser rule as make_frag)
+    const vec2 astuv = mk2(float((double(x) + 0.5)/double(P.W)), float((double(y) + 0.5)/double(P.H)));
+    vec3 rgb;
+    if (P.subsample == 1) {
+        rgb = screen_bilinear(P, astuv);
+    } else {
+        const int kernel = P.subsample;
+        vec3 acc = mk3(0.0f);
+        vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
+        vec2 corner = astuv - (pixel_size/2.0f);
+        vec2 origin = corner + (pixel_size/float(kernel))/2.0f;
+        for (int sx = 0; sx < kernel; sx++)
+            for (int sy = 0; sy < kernel; sy++) {
+                vec2 offset = (pixel_size/float(kernel))*mk2(float(sx), float(sy));
+                acc = acc + screen_bilinear(P, origin + offset);
+            }
+        rgb = acc/float(kernel*kernel);
+    }
+    const size_t idx = size_t(y)*size_t(P.W) + size_t(x);
+    if (P.comps == 4) {
+        reinterpret_cast<uchar4*>(P.dst)[idx] = make_uchar4(to_unorm8(rgb.x), to_unorm8(rgb.y), to_unorm8(rgb.z), 255);
+    } else {
+        unsigned char* p = P.dst + idx*3;
+        p[0] = to_unorm8(rgb.x); p[1] = to_unorm8(rgb.y); p[2] = to_unorm8(rgb.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// texture() probe (tests of the sampler rules)
+
+template <bool HW>
+__global__ void sample_kernel(DevSampler s, const float2* uv, int n, float4* out) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vec4 c = texture<HW>(s, mk2(uv[i].x, uv[i].y));
+    out[i] = make_float4(c.x, c.y, c.z, c.w);
+}
+
+extern "C" int sfb_tex_sample(sfb_tex* tex, const float* uv_dev, int n, int flags, float* out_dev) {
+    SFB_REQUIRE(tex && uv_dev && out_dev && n >= 0, "sfb_tex_sample: bad argument");
+    if (n == 0) return SFB_OK;
+    const DevSampler s = tex->dev();
+    if (flags & SFB_FILTER_HARDWARE)
+        sample_kernel<true><<<(n + 255)/256, 256, 0, tex->ctx->stream>>>(s, (const float2*)uv_dev, n, (float4*)out_dev);
+    else
+        sample_kernel<false><<<(n + 255)/256, 256, 0, tex->ctx->stream>>>(s, (const float2*)uv_dev, n, (float4*)out_dev);
+    SFB_LAUNCH_CHECK(tex->ctx);
+    return SFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene registry
+
+static const sfb_scene_info SCENES[SFB_SCENE_COUNT] = {
+    {"default",    "shaderflow/resources/shaders/fragment/default.glsl", 0, {}, 0, {}},
+    {"shadertoy",  "examples/basic/shaders/shadertoy.frag",               0, {}, 0, {}},
+    {"visualizer", "examples/basic/shaders/visualizer.frag", 2, {"iAudioVolume", "iAudioSTD"},
+                   3, {"background", "iSpectrogram", "iWaveform"}},
+    {"bars",       "examples/basic/shaders/bars.frag",      0, {}, 1, {"iSpectrogram"}},
+    {"waveform",   "examples/basic/shaders/waveform.frag",  0, {}, 1, {"iWaveform"}},
+    {"mandelbrot", "examples/fractals/shaders/mandelbrot.frag", 0, {}, 0, {}},
+    {"tetration",  "examples/fractals/shaders/tetration.frag",  0, {}, 0, {}},
+    {"raymarch",   "examples/basic/shaders/raymarch.frag",      0, {}, 0, {}},
+};
+
+extern "C" int sfb_scene_lookup(const char* name, int* scene) {
+    SFB_REQUIRE(name && scene, "sfb_scene_lookup: null argument");
+    for (int i = 0; i < SFB_SCENE_COUNT; i++)
+        if (std::string(SCENES[i].name) == name) { *scene = i; return SFB_OK; }
+    SFB_FAIL(SFB_ENOTFOUND, "sfb_scene_lookup: no built-in scene named '%s'", name);
+}
+
+extern "C" int sfb_scene_info_get(int scene, sfb_scene_info* info) {
+    SFB_REQUIRE(info && scene >= 0 && scene < SFB_SCENE_COUNT, "sfb_scene_info_get: bad scene %d", scene);
+    *info = SCENES[scene];
+    return SFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launchers
+
+static int fill_params(RenderParams& P, const char* who, int scene, const sfb_uniforms* uniforms,
+                       sfb_tex* const* samplers, int n_samplers) {
+    SFB_REQUIRE(scene >= 0 && scene < SFB_SCENE_COUNT, "%s: bad scene %d", who, scene);
+    SFB_REQUIRE(uniforms, "%s: null uniforms", who);
+    SFB_REQUIRE(n_samplers >= SCENES[scene].n_samplers && n_samplers <= SFB_MAX_SAMPLERS,
+        "%s: scene '%s' needs %d samplers, got %d", who, SCENES[scene].name, SCENES[scene].n_samplers, n_samplers);
+    P.u = *uniforms;
+    for (int i = 0; i < n_samplers; i++) {
+        SFB_REQUIRE(samplers && samplers[i], "%s: sampler %d is null", who, i);
+        P.tex[i] = samplers[i]->dev();
+        SFB_REQUIRE(P.tex[i].lin, "%s: sampler %d has no storage", who, i);
+    }
+    return SFB_OK;
+}
+
+template <template <int, bool> class Launch, typename... A>
+static void dispatch(int scene, bool hw, A... a) {
+    #define SFB_CASE(S) case S: hw ? Launch<S, true>::run(a...) : Launch<S, false>::run(a...); break;
+    switch (scene) {
+        SFB_CASE(SFB_SCENE_DEFAULT) SFB_CASE(SFB_SCENE_SHADERTOY) SFB_CASE(SFB_SCENE_VISUALIZER)
+        SFB_CASE(SFB_SCENE_BARS) SFB_CASE(SFB_SCENE_WAVEFORM) SFB_CASE(SFB_SCENE_MANDELBROT)
+        SFB_CASE(SFB_SCENE_TETRATION) SFB_CASE(SFB_SCENE_RAYMARCH)
+    }
+    #undef SFB_CASE
+}
+
+template <int S, bool HW> struct LaunchScreen {
+    static void run(const RenderParams& P, cudaStream_t st) {
+        dim3 block(32, 8), grid((P.Wr + 31)/32, (P.Hr + 7)/8);
+        screen_kernel<S, HW><<<grid, block, 0, st>>>(P);
+    }
+};
+template <int S, bool HW> struct LaunchFrame {
+    static void run(const RenderParams& P, cudaStream_t st) {
+        dim3 block(TILE_X, TILE_Y), grid((P.W + TILE_X - 1)/TILE_X, (P.H + TILE_Y - 1)/TILE_Y);
+        frame_kernel<S, HW><<<grid, block, 0, st>>>(P);
+    }
+};
+
+extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                                 sfb_tex* const* samplers, int n_samplers, int flags,
+                                 int target_w, int target_h, void* dst_rgba8_dev, float* dst_f32_dev) {
+    SFB_REQUIRE(ctx && dst_rgba8_dev, "sfb_render_screen: null ctx or destination");
+    SFB_REQUIRE(target_w > 0 && target_h > 0, "sfb_render_screen: bad target %dx%d", target_w, target_h);
+    RenderParams P{};
+    if (int e = fill_params(P, "sfb_render_screen", scene, uniforms, samplers, n_samplers)) return e;
+    P.Wr = target_w; P.Hr = target_h;
+    P.W = int(uniforms->iResolution[0]); P.H = int(uniforms->iResolution[1]);
+    P.inv_Wr = 1.0/double(target_w); P.inv_Hr = 1.0/double(target_h);
+    P.dst = static_cast<unsigned char*>(dst_rgba8_dev); P.dst_f32 = dst_f32_dev;
+    dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+extern "C" int sfb_render_final(sfb_ctx* ctx, const void* screen_rgba8_dev, int screen_w, int screen_h,
+                                int width, int height, int subsample, int components, void* dst_dev) {
+    SFB_REQUIRE(ctx && screen_rgba8_dev && dst_dev, "sfb_render_final: null argument");
+    SFB_REQUIRE(screen_w > 0 && screen_h > 0 && width > 0 && height > 0, "sfb_render_final: bad size");
+    SFB_REQUIRE(subsample >= 1 && subsample <= 16, "sfb_render_final: subsample %d out of range", subsample);
+    SFB_REQUIRE(components == 3 || components == 4, "sfb_render_final: components must be 3 or 4");
+    FinalParams P{static_cast<const unsigned char*>(screen_rgba8_dev), screen_w, screen_h,
+                  width, height, subsample, components, static_cast<unsigned char*>(dst_dev)};
+    dim3 block(32, 8), grid((width + 31)/32, (height + 7)/8);
+    final_kernel<<<grid, block, 0, ctx->stream>>>(P);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                                sfb_tex* const* samplers, int n_samplers, int flags,
+                                int width, int height, int ssaa, int subsample, int components, void* dst_dev) {
+    SFB_REQUIRE(ctx && dst_dev, "sfb_render_frame: null ctx or destination");
+    SFB_REQUIRE(width > 0 && height > 0, "sfb_render_frame: bad size %dx%d", width, height);
+    SFB_REQUIRE(ssaa >= 1 && ssaa <= 16, "sfb_render_frame: ssaa %d out of range", ssaa);
+    SFB_REQUIRE(subsample == ssaa || 2*subsample == ssaa,
+        "sfb_render_frame: final.glsl is a box filter only for subsample == ssaa or ssaa/2 "
+        "(got ssaa=%d subsample=%d); use sfb_render_screen + sfb_render_final", ssaa, subsample);
+    SFB_REQUIRE(components == 3 || components == 4, "sfb_render_frame: components must be 3 or 4");
+    RenderParams P{};
+    if (int e = fill_params(P, "sfb_render_frame", scene, uniforms, samplers, n_samplers)) return e;
+    P.W = width; P.H = height; P.ssaa = ssaa; P.subsample = subsample; P.comps = components;
+    P.Wr = width*ssaa; P.Hr = height*ssaa;
+    P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
+    P.dst = static_cast<unsigned char*>(dst_dev);
+    dispatch<LaunchFrame>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}

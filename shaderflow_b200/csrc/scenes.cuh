@@ -1,0 +1,290 @@
+// scenes.cuh — the reference's GLSL fragment shaders transliterated to CUDA device functions.
+// Each `scene_*` is `void main()` of the cited file with fragColor returned; uniforms come from the
+// kernel parameter block, varyings from `Frag` (vertex/default.glsl:1-17), samplers by slot
+// (order reported by sfb_scene_info_get). Float loop counters are evaluated in strict IEEE float32.
+#pragma once
+#include "glsl.cuh"
+#include "sampler.cuh"
+
+namespace glsl {
+
+struct RenderParams {
+    sfb_uniforms u;
+    DevSampler tex[SFB_MAX_SAMPLERS];
+    int Wr, Hr;              // fragments of the iScreen target (render resolution)
+    int W, H;                // final resolution
+    int ssaa, subsample, comps;
+    double inv_Wr, inv_Hr;   // 1/Wr, 1/Hr
+    unsigned char* dst;
+    float* dst_f32;
+};
+
+struct Frag { vec2 agluv, gluv, astuv, stuv, stxy, glxy; };
+
+// iAspectRatio macro (shaderflow.glsl:16)
+SFB_DEV float aspect_ratio(const sfb_uniforms& u) { return u.iResolution[0]/u.iResolution[1]; }
+
+// The rasteriser: vertex/default.glsl:8-16 at the quad corners (shader.py:127-128), interpolated
+// affinely (float64) to the centre of fragment (i, j), rounded once — same spec as the oracle.
+SFB_DEV Frag make_frag(const RenderParams& P, int i, int j) {
+    const double tx = (double(i) + 0.5)*P.inv_Wr, ty = (double(j) + 0.5)*P.inv_Hr;
+    const float W = P.u.iResolution[0], H = P.u.iResolution[1];
+    const float a = aspect_ratio(P.u);
+    auto lerp = [](double x0, double x1, double t) { return float(x0 + (x1 - x0)*t); };
+    Frag f;
+    f.agluv = mk2(lerp(-1.0, 1.0, tx), lerp(-1.0, 1.0, ty));
+    f.gluv  = mk2(lerp(double(-1.0f*a), double(1.0f*a), tx), f.agluv.y);
+    f.astuv = mk2(lerp(0.0, 1.0, tx), lerp(0.0, 1.0, ty));
+    f.stuv  = mk2(lerp(double((-a + 1.0f)/2.0f), double((a + 1.0f)/2.0f), tx), f.astuv.y);
+    f.stxy  = mk2(lerp(1.0, double(W*1.0f + 1.0f), tx), lerp(1.0, double(H*1.0f + 1.0f), ty));
+    f.glxy  = mk2(lerp(double(1.0f - W/2.0f), double((W + 1.0f) - W/2.0f), tx),
+                  lerp(double(1.0f - H/2.0f), double((H + 1.0f) - H/2.0f), ty));
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// camera.glsl:55-155
+
+struct Camera {
+    vec2 gluv, agluv, stuv, astuv;
+    vec3 origin, target;
+    bool out_of_bounds;
+};
+
+SFB_DEV vec3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+
+SFB_DEV Camera get_camera(const sfb_uniforms& u, const Frag& f) {
+    const vec3 pos = ld3(u.iCameraPosition), right = ld3(u.iCameraRight), up = ld3(u.iCameraUpward);
+    const vec3 fwd = ld3(u.iCameraForward), back = fwd*(-1.0f);
+    const float asp = aspect_ratio(u);
+    auto rectangle = [&](vec2 g, float size) { return size*(g.x*right + g.y*up); };                  // :55-57
+    auto ray_origin = [&](vec3 p, vec2 g) {                                                           // :59-64
+        return p + rectangle(g, u.iCameraZoom*u.iCameraIsometric) + (back*u.iCameraOrbital) + (back*u.iCameraDolly); };
+    auto ray_target = [&](vec3 p, vec2 g) {                                                           // :66-71
+        return p + rectangle(g, u.iCameraZoom) + (back*u.iCameraOrbital) + (fwd*u.iCameraFocalLength); };
+
+    Camera c;
+    if (u.iCameraProjection == 0) {
+        c.origin = ray_origin(pos, f.gluv);
+        c.target = ray_target(pos, f.gluv);
+    } else if (u.iCameraProjection == 1) {                                                            // :101-110
+        float sg = sign(f.agluv.x);
+        vec2 g = f.gluv - sg*mk2(asp/2.0f, 0.0f);
+        vec3 p = pos + (sg*u.iCameraSeparation)*right;
+        c.origin = ray_origin(p, g);
+        c.target = ray_target(p, g);
+    } else {                                                                                          // :113-127
+        float inclination = u.iCameraZoom*(PI*f.agluv.y/2.0f);
+        float azimuth     = u.iCameraZoom*(PI*f.agluv.x/1.0f);
+        vec3 t = rotate3d(fwd, right, -inclination);
+        t = rotate3d(t, up, azimuth);
+        c.origin = pos;
+        c.target = pos + t;
+    }
+    // CameraRay2D (:73-91): plane through (0,0,1), normal (0,0,1)
+    const vec3 pp = mk3(0.0f, 0.0f, 1.0f), pn = mk3(0.0f, 0.0f, 1.0f);
+    float num = dot(pp - c.origin, pn);
+    float den = dot(c.target - c.origin, pn);
+    float t = num/den;
+    c.out_of_bounds = (t < 0.0f) || (fabsf(f.gluv.x) > u.iWantAspect);
+    vec3 hit = c.origin + (t*(c.target - c.origin));
+    c.gluv  = xy(hit);
+    c.agluv = c.gluv/mk2(asp, 1.0f);
+    c.stuv  = gluv2stuv(c.gluv);
+    c.astuv = gluv2stuv(c.agluv);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resources/shaders/fragment/default.glsl:10-48
+
+template <bool HW>
+SFB_DEV vec4 scene_default(const RenderParams& P, const Frag& f) {
+    Camera cam = get_camera(P.u, f);
+    vec2 uv = cam.gluv;
+    if (cam.out_of_bounds) return mk4(mk3(0.15f), 1.0f);
+    vec3 rgb = mk3(0.0f);
+    float angle = atan2_pos(uv.y, uv.x);
+    vec3 color = 0.3f + hsv2rgb(angle + (2.0f*TAU*P.u.iTau) - (PI/4.0f), 1.0f, 1.0f);
+    float circle = (1.333f*length(uv) - 1.0f);
+    float width = 2.0f*fabsf(1.0f/(circle*circle))*1e-4f;
+    if (circle < 0.0f) {
+        rgb = rgb + mk3(0.18f);
+    } else {
+        const float grid = 8.0f;
+        bool odd = mod(floorf(uv.x*grid/2.0f) + floorf(uv.y*grid/2.0f), 2.0f) > 0.5f;
+        rgb = rgb + (odd ? mk3(0.22f) : mk3(0.20f));
+    }
+    rgb = rgb + (width*color);
+    vec2 away = f.astuv*(1.0f - yx(f.astuv));
+    float linear = 50.0f*(away.x*away.y);
+    rgb = rgb*clamp(powf(linear, 0.1f), 0.0f, 1.0f);
+    return mk4(rgb, 1.0f);
+}
+
+// examples/basic/shaders/shadertoy.frag:62-66
+template <bool HW>
+SFB_DEV vec4 scene_shadertoy(const RenderParams& P, const Frag& f) {
+    float t = P.u.iTime;
+    vec3 col = mk3(0.5f + 0.5f*cosf(t + f.stuv.x + 0.0f), 0.5f + 0.5f*cosf(t + f.stuv.y + 2.0f),
+                   0.5f + 0.5f*cosf(t + f.stuv.x + 4.0f));
+    return mk4(col, 1.0f);
+}
+
+// examples/basic/shaders/visualizer.frag:6-74
+// extra[0].x = iAudioVolume, extra[1].x = iAudioSTD; samplers: background, iSpectrogram, iWaveform
+template <bool HW>
+SFB_DEV vec4 scene_visualizer(const RenderParams& P, const Frag& f) {
+    const float iTime = P.u.iTime, iAudioVolume = P.u.extra[0][0], iAudioSTD = P.u.extra[1][0];
+    const DevSampler& background = P.tex[0];
+    Camera cam = get_camera(P.u, f);
+    vec2 uv = cam.gluv;
+    vec3 space = mk3(1.0f, 11.0f, 26.0f)/255.0f;
+    if (cam.out_of_bounds) return mk4(space, 0.0f);
+
+    vec2 background_uv = zoom(gluv2stuv(uv), 0.95f + 0.01f*sinf(iTime) - 0.02f*iAudioVolume - 0.03f, mk2(0.5f));
+    background_uv = background_uv + 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
+    vec4 fragColor = stexture<HW>(background, background_uv);
+    {
+        float intensity = 0.01f*clamp(powf(iAudioVolume, 2.5f), 0.0f, 0.3f);
+        float quality = 10.0f, directions = 8.0f;
+        vec4 color = fragColor;
+        // Strict float32 counters: 9 angles × 10 walks
+        for (float angle = 0.0f; angle < TAU; angle += TAU/directions) {
+            vec2 dir = mk2(cosf(angle), sinf(angle));
+            for (float walk = 1.0f/quality; walk <= 1.001f; walk += 1.0f/quality) {
+                vec2 displacement = dir*walk*intensity;
+                color = color + stexture<HW>(background, background_uv + displacement);
+            }
+        }
+        fragColor = color/(quality*directions);
+    }
+    fragColor = fragColor*(1.0f + 5.0f*iAudioSTD*powf(clamp(length(f.agluv) - 0.3f, 0.0f, 1.0f), 6.0f));
+
+    vec2 music_uv = rotate2d_mul(-PI/2.0f, uv);
+    music_uv = music_uv*(1.0f - 0.4f*powf(fabsf(iAudioVolume), 0.5f));
+    float radius = 0.17f;
+
+    float circle = fabsf(atan1n(music_uv));
+    vec4 s = texture<HW>(P.tex[1], mk2(0.0f, circle));
+    vec2 freq = mk2(sqrtf(s.x/1000.0f), sqrtf(s.y/1000.0f));
+    freq = freq*(0.05f + 3.0f*smoothstep(0.0f, 2.0f, circle));
+
+    vec3 rgb = xyz(fragColor);
+    if (length(music_uv) < radius) {
+        rgb = rgb*0.5f;
+    } else {
+        float bar = (music_uv.y < 0.0f) ? freq.x : freq.y;
+        float r = radius + 0.5f*bar;
+        if (length(music_uv) < r) rgb = mix(rgb, mk3(1.0f), smoothstep(0.0f, 1.0f, 0.5f + bar));
+        else                      rgb = rgb*powf((length(music_uv) - r)*0.5f, 0.05f);
+    }
+    rgb = mix(rgb, space, smoothstep(0.0f, 1.0f, length(uv)/20.0f));
+
+    vec2 vig = f.astuv*(1.0f - yx(f.astuv));
+    rgb = rgb*powf(vig.x*vig.y*20.0f, 0.1f + 0.15f*iAudioVolume);
+    fragColor = mk4(rgb, 1.0f);
+
+    vec4 w = texture<HW>(P.tex[2], mk2(f.astuv.x, 0.0f));
+    vec2 wave = mk2(0.2f*w.x, 0.2f*w.y);
+    if (1.0f - f.gluv.y < wave.x) fragColor = fragColor*0.8f;
+    if (1.0f + f.gluv.y < wave.y) fragColor = fragColor*0.8f;
+    return fragColor;
+}
+
+// examples/basic/shaders/bars.frag:5-22 — samplers: iSpectrogram
+template <bool HW>
+SFB_DEV vec4 scene_bars(const RenderParams& P, const Frag& f) {
+    vec4 s = texture<HW>(P.tex[0], yx(f.astuv));
+    vec2 intensity = mk2(sqrtf(s.x)/120.0f, sqrtf(s.y)/120.0f);
+    vec3 rgb = mk3(0.0f);
+    if (f.astuv.y < intensity.x) rgb = rgb + mk3(1.0f, 0.0f, 0.0f);
+    if (f.astuv.y < intensity.y) rgb = rgb + mk3(0.0f, 1.0f, 0.0f);
+    if (f.astuv.y < (intensity.y + intensity.x)/2.0f) rgb = rgb + mk3(0.0f, 0.0f, 1.0f);
+    rgb = rgb + mk3(0.0f, 0.0f, 0.4f*(intensity.x + intensity.y)*(1.0f - f.astuv.y));
+    return mk4(rgb, 1.0f);
+}
+
+// examples/basic/shaders/waveform.frag:5-19 — samplers: iWaveform
+template <bool HW>
+SFB_DEV vec4 scene_waveform(const RenderParams& P, const Frag& f) {
+    vec4 w = texture<HW>(P.tex[0], mk2(f.astuv.x, 0.0f));
+    vec4 c = mk4(mk3(0.2f), 1.0f);
+    float ay = fabsf(f.gluv.y);
+    if (ay < w.x) c.x = 1.0f;
+    if (ay < w.y) c.y = 1.0f;
+    if (ay < (w.x + w.y)/2.0f) c.z = 1.0f;
+    return c;
+}
+
+// examples/fractals/shaders/mandelbrot.frag:10-31
+template <bool HW>
+SFB_DEV vec4 scene_mandelbrot(const RenderParams& P, const Frag& f) {
+    Camera cam = get_camera(P.u, f);
+    if (cam.out_of_bounds) return mk4(palette_magma(0.0f), 1.0f);
+    vec2 z = cam.gluv - mk2(0.5f, 0.0f);
+    vec2 c = z;
+    int quality = int(1000.0f*P.u.iQuality);
+    int iter = 0;
+    for (; iter < quality; iter++) {
+        if (length(z) > 3.0f) break;
+        z = mk2(z.x*z.x - z.y*z.y, z.x*z.y + z.y*z.x) + c;
+    }
+    float t = powf(1.0f - float(iter)/float(quality), 20.0f);
+    return mk4(palette_magma(t), 1.0f);
+}
+
+// examples/fractals/shaders/tetration.frag:28-55
+template <bool HW>
+SFB_DEV vec4 scene_tetration(const RenderParams& P, const Frag& f) {
+    Camera cam = get_camera(P.u, f);
+    float Cx = cam.gluv.x, Cy = cam.gluv.y;
+    float Cr = sqrtf(Cx*Cx + Cy*Cy), Ct = atan2f(Cy, Cx);
+    float Zx = Cx, Zy = Cy, Zr = Cr;
+    const int MAX_STEPS = 67;
+    int it = 0;
+    for (it = 0; it < MAX_STEPS; it++) {
+        float r = powf(Cr, Zx)*expf(-Zy*Ct);
+        float t = Zy*logf(Cr) + (Zx*Ct);
+        Zr = r; Zx = r*cosf(t); Zy = r*sinf(t);
+        if (Zr > 100.0f) break;
+    }
+    float k = float(it/MAX_STEPS);                 // integer division, tetration.frag:50
+    float theta = atan2n(Zy, Zx);
+    return mk4(hsv2rgb(theta, 1.0f, k), 1.0f);
+}
+
+// examples/basic/shaders/raymarch.frag:33-60
+template <bool HW>
+SFB_DEV vec4 scene_raymarch(const RenderParams& P, const Frag& f) {
+    Camera cam = get_camera(P.u, f);
+    vec3 origin = cam.origin;
+    vec3 forward = normalize(cam.target - origin);
+    float traveled = 0.0f, walk = 0.0f;
+    int steps;
+    for (steps = 0; steps < 100; steps++) {
+        vec3 point = origin + (forward*traveled);
+        float sdf = 2.0f*100.0f;
+        for (int i = 2; i < 8; i++)
+            sdf = fminf(sdf, sdBox(point, mk3(0.0f, 0.0f, float(i)), mk3(float(i - 1))));
+        walk = sdf;
+        traveled += walk;
+        if (walk < 0.001f || walk > 100.0f) break;
+    }
+    return mk4(mk3(1.0f - sqrtf(float(steps))*0.1f), 1.0f);
+}
+
+template <int SCENE, bool HW>
+SFB_DEV vec4 shade(const RenderParams& P, const Frag& f) {
+    if constexpr (SCENE == SFB_SCENE_DEFAULT)    return scene_default<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_SHADERTOY)  return scene_shadertoy<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_VISUALIZER) return scene_visualizer<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_BARS)       return scene_bars<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_WAVEFORM)   return scene_waveform<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_MANDELBROT) return scene_mandelbrot<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_TETRATION)  return scene_tetration<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_RAYMARCH)   return scene_raymarch<HW>(P, f);
+    return mk4(0.0f);
+}
+
+} // namespace glsl

@@ -1,0 +1,62 @@
+// sfb_internal.h — shared between the translation units of libsfb200.so (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/sfb200.h"
+
+// Thread-local error message (sfb_last_error)
+void sfb_set_error(const char* fmt, ...);
+
+#define SFB_FAIL(code, ...) do { sfb_set_error(__VA_ARGS__); return (code); } while (0)
+#define SFB_REQUIRE(cond, ...) do { if (!(cond)) SFB_FAIL(SFB_EINVAL, __VA_ARGS__); } while (0)
+#define SFB_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    sfb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    return SFB_ECUDA; } } while (0)
+#define SFB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; SFB_CUDA(cudaGetLastError()); } while (0)
+
+struct sfb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // Lazily built device tables of the STFT (twiddles per fft_n, windows per (kind, fft_n))
+    float2* twiddle[16] = {};
+    float*  window[3][16] = {};
+    // Scratch for sfb_audio_track
+    void*  scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+int sfb_ctx_scratch(sfb_ctx* ctx, size_t bytes, void** out);
+
+// What a kernel sees of a texture (passed by value inside the kernel parameter block)
+struct DevSampler {
+    unsigned long long hw;   // cudaTextureObject_t, 0 when only the linear mirror is valid
+    const void* lin;         // [h][w][padded] texels, tightly packed
+    int w, h;
+    int padded;              // components as stored: 1, 2 or 4
+    int comps;               // components the user declared (3 → alpha reads 1)
+    int dtype;               // SFB_DTYPE_*
+    int filter;              // SFB_FILTER_NEAREST / LINEAR
+    int rx, ry;              // repeat (1) or clamp-to-edge (0)
+};
+
+struct sfb_tex {
+    sfb_ctx* ctx = nullptr;
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t obj = 0;
+    void* lin = nullptr;
+    const void* external = nullptr;
+    int w = 0, h = 0, comps = 0, padded = 0, dtype = 0, filter = 0, rx = 1, ry = 1;
+    size_t texel_bytes() const { return size_t(padded)*(dtype == SFB_DTYPE_U8 ? 1 : (dtype == SFB_DTYPE_F16 ? 2 : 4)); }
+    DevSampler dev() const {
+        DevSampler s;
+        s.hw = external ? 0ull : (unsigned long long)obj;
+        s.lin = external ? external : lin;
+        s.w = w; s.h = h; s.padded = padded; s.comps = comps; s.dtype = dtype; s.filter = filter; s.rx = rx; s.ry = ry;
+        return s;
+    }
+};
