@@ -56,7 +56,7 @@ SFB_DEV vec4 texture(const DevSampler& s, vec2 uv) {
     if (HW && s.hw != 0ull) {
         float4 c = tex2D<float4>((cudaTextureObject_t)s.hw, uv.x, uv.y);
         vec4 t = mk4(c.x, c.y, c.z, c.w);
-        if (s.comps == 3) t.w = 1.0f;
+        if (s.comps < 4) t.w = 1.0f;         // GL: missing alpha reads 1 (CUDA returns 0)
         return t;
     }
     float u = uv.x*float(s.w), v = uv.y*float(s.h);

@@ -216,9 +216,11 @@ def test_large_frame_properties(ctx, scene_inputs):
     ctx.sync()
     a, b = a.cpu().numpy(), b.cpu().numpy()
     assert np.array_equal(a, b)
-    assert np.array_equal(a[..., 0], a[..., 2][:, :]) is False or True
     # green channel depends on y only; red/blue on x only
     assert (a[..., 1] == a[:, :1, 1]).all() and (a[..., 0] == a[:1, :, 0]).all()
     uo = G.Uniforms(iTime=1.25, iResolution=(W4, H4), iWantAspect=W4/H4)
-    ref = G.render("shadertoy", uo, {}, W4, 8, ssaa=2.0, subsample=2)   # 8 rows suffice for the x profile
-    assert np.abs(a[0, :, 0].astype(int) - ref["final_u8"][0, :, 0].astype(int)).max() <= 1
+    # oracle on the two bottom sub-sample rows only (the x profile): shade, 8-bit store, 2x2 box, store
+    sub = G.to_unorm8(G.frag_shadertoy(uo, G.varyings(uo, 2*W4, 2*H4, rows=slice(0, 2)), {}))[..., :3].astype(np.float32)
+    box = G.to_unorm8(sub.reshape(1, 2, W4, 2, 3).mean(axis=(1, 3))/255.0)
+    assert np.abs(a[0].astype(int) - box[0].astype(int)).max() <= 1
+    assert (a[0] == box[0]).mean() > 0.9
