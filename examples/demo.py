@@ -1,0 +1,109 @@
+"""Example scenes for the CUDA backend — the user-side code of the reference's examples/basic/demo.py
+and examples/fractals/fractals.py (same class names, same `build()` logic against the same API), with
+two practical differences: assets the reference downloads are replaced by synthetic ones unless a path
+is given, and audio is injected with `scene.audio.load(pcm, samplerate)` (the reference's examples ship
+placeholder paths, demo.py:164,177,196).
+
+    import shaderflow_b200; shaderflow_b200.install_alias()
+    from examples.demo import Visualizer
+    scene = Visualizer(); scene.initialize(); scene.audio.load(pcm, 44100)
+    scene.main(width=3840, height=2160, ssaa=2, output="out.mp4")
+"""
+from pathlib import Path
+
+import numpy as np
+
+import shaderflow_b200
+shaderflow_b200.install_alias()
+
+from shaderflow.scene import ShaderScene          # noqa: E402
+from shaderflow.texture import ShaderTexture      # noqa: E402
+
+shaders: Path = (Path(__file__).parent/"shaders")
+
+
+def synthetic_background(width: int = 1920, height: int = 1080, seed: int = 1) -> np.ndarray:
+    """Deterministic stand-in for the downloaded wallpaper: smooth colour field + grain, RGB8, top row first"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width].astype(np.float64)
+    x /= width; y /= height
+    img = np.stack([0.5 + 0.5*np.sin(6.0*x + 2.0*np.cos(5.0*y)),
+                    0.5 + 0.5*np.sin(4.0*y + 3.0*x*x + 1.0),
+                    0.5 + 0.5*np.cos(9.0*(x - 0.5)*(y - 0.5) + 2.0)], -1)
+    img += rng.uniform(-0.08, 0.08, img.shape)
+    return (np.clip(img, 0, 1)*255).round().astype(np.uint8)
+
+
+class Basic(ShaderScene):
+    """Simplest ShaderScene"""
+    ...
+
+
+class ShaderToy(ShaderScene):
+    """ShaderToy Default Shader"""
+    def build(self):
+        self.shader.fragment = (shaders/"shadertoy.frag")
+
+
+class Waveform(ShaderScene):
+    """Audio Waveform Oscilloscope demo"""
+    def build(self):
+        from shaderflow.audio import ShaderAudio
+        from shaderflow.audio.waveform import ShaderWaveform
+        self.audio = ShaderAudio(scene=self, name="iAudio", file="/path/to/audio.ogg")
+        self.waveform = ShaderWaveform(scene=self, audio=self.audio, smooth=False)
+        self.shader.fragment = (shaders/"waveform.frag")
+
+
+class MusicBars(ShaderScene):
+    """Basic music bars"""
+    def build(self):
+        from shaderflow.audio import ShaderAudio
+        from shaderflow.audio.spectrogram import ShaderSpectrogram
+        from shaderflow.piano import PianoNote
+        self.audio = ShaderAudio(scene=self, name="iAudio", file="/path/to/audio.ogg")
+        self.spectrogram = ShaderSpectrogram(scene=self, audio=self.audio, length=0)
+        self.spectrogram.from_notes(start=PianoNote.from_frequency(20), end=PianoNote.from_frequency(18000), piano=True)
+        self.shader.fragment = (shaders/"bars.frag")
+
+
+class Visualizer(ShaderScene):
+    """Radial Bars Music Visualizer Scene"""
+    background = None   # path / numpy image; synthetic when None
+
+    def build(self):
+        from shaderflow.audio import ShaderAudio
+        from shaderflow.audio.spectrogram import ShaderSpectrogram
+        from shaderflow.audio.waveform import ShaderWaveform
+        from shaderflow.piano import PianoNote
+        self.audio = ShaderAudio(scene=self, name="iAudio", file="/path/to/audio.opus")
+        self.waveform = ShaderWaveform(scene=self, audio=self.audio)
+        self.spectrogram = ShaderSpectrogram(scene=self, length=0, audio=self.audio, smooth=False)
+        self.spectrogram.from_notes(start=PianoNote.from_frequency(20), end=PianoNote.from_frequency(14000), piano=True)
+        image = self.background if self.background is not None else synthetic_background()
+        self.back = ShaderTexture(scene=self, name="background").from_image(image)
+        self.shader.fragment = (shaders/"visualizer.frag")
+
+    def handle(self, message) -> None:
+        from shaderflow.message import ShaderMessage
+        ShaderScene.handle(self, message)
+        if isinstance(message, ShaderMessage.Window.FileDrop):
+            self.back.from_image(message.first)
+
+
+class RayMarch(ShaderScene):
+    """Ray Marching demo"""
+    def build(self):
+        self.shader.fragment = (shaders/"raymarch.frag")
+
+
+class Mandelbrot(ShaderScene):
+    """Mandelbrot fractal"""
+    def build(self):
+        self.shader.fragment = (shaders/"mandelbrot.frag")
+
+
+class Tetration(ShaderScene):
+    """Complex tetration fractal"""
+    def build(self):
+        self.shader.fragment = (shaders/"tetration.frag")

@@ -135,6 +135,10 @@ int sfb_tex_write(sfb_tex* tex, const void* data, int on_device, int x, int y, i
  * Pass NULL to go back to the texture's own storage. */
 int sfb_tex_bind_external(sfb_tex* tex, const void* data_dev);
 int sfb_tex_read(sfb_tex* tex, void* data_host);          /* blocks; debugging / tests */
+/* Render-target use (the FBO of texture.py:266-267): device pointer of the texture's own linear storage,
+ * [height][width][padded components]. Kernels that write it make the cudaArray copy stale, so the texture
+ * samples through the exact (linear-mirror) path until the next sfb_tex_write. */
+int sfb_tex_storage(sfb_tex* tex, void** data_dev, size_t* bytes);
 /* texture(sampler, uv) probe: n normalised coordinates uv_dev [n][2] → out_dev [n][4] float32, with the
  * texture's filter / wrap state and SFB_FILTER_EXACT or SFB_FILTER_HARDWARE (parity tests of the sampler) */
 int sfb_tex_sample(sfb_tex* tex, const float* uv_dev, int n, int flags, float* out_dev);

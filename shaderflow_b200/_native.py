@@ -87,6 +87,7 @@ _PROTOTYPES = dict(
     sfb_tex_write=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     sfb_tex_bind_external=(c_int, [c_void_p, c_void_p]),
     sfb_tex_read=(c_int, [c_void_p, c_void_p]),
+    sfb_tex_storage=(c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
     sfb_tex_sample=(c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     sfb_scene_lookup=(c_int, [c_char_p, POINTER(c_int)]),
     sfb_scene_info_get=(c_int, [c_int, POINTER(SceneInfo)]),
@@ -209,6 +210,12 @@ class Texture:
         out = np.empty((self.height, self.width, padded), dt)
         check(lib().sfb_tex_read(self.handle, _ptr(out)))
         return out
+
+    def storage(self) -> tuple[int, int]:
+        """(device pointer, bytes) of the linear storage, for use as a render target"""
+        p, n = c_void_p(), c_size_t()
+        check(lib().sfb_tex_storage(self.handle, byref(p), byref(n)))
+        return p.value, n.value
 
     def sample(self, uv, out, flags: int = FILTER_EXACT) -> None:
         """uv (n, 2) f32 cuda → out (n, 4) f32 cuda"""

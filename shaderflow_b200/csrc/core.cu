@@ -247,12 +247,21 @@ extern "C" int sfb_tex_write(sfb_tex* t, const void* data, int on_device, int x,
                                cudaMemcpyDeviceToDevice, ctx->stream));
     SFB_CUDA(cudaMemcpy2DToArrayAsync(t->array, size_t(x)*texel, size_t(y), packed, size_t(w)*texel,
                                       size_t(w)*texel, size_t(h), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (t->array_stale && w == t->w && h == t->h) t->array_stale = false;
     return SFB_OK;
 }
 
 extern "C" int sfb_tex_bind_external(sfb_tex* t, const void* data_dev) {
     SFB_REQUIRE(t, "sfb_tex_bind_external: null texture");
     t->external = data_dev;
+    return SFB_OK;
+}
+
+extern "C" int sfb_tex_storage(sfb_tex* t, void** data_dev, size_t* bytes) {
+    SFB_REQUIRE(t && data_dev, "sfb_tex_storage: null argument");
+    t->array_stale = true;
+    *data_dev = t->lin;
+    if (bytes) *bytes = size_t(t->w)*size_t(t->h)*t->texel_bytes();
     return SFB_OK;
 }
 

@@ -50,11 +50,12 @@ struct sfb_tex {
     cudaTextureObject_t obj = 0;
     void* lin = nullptr;
     const void* external = nullptr;
+    bool array_stale = false;          // rendered into through sfb_tex_storage: cudaArray copy is old
     int w = 0, h = 0, comps = 0, padded = 0, dtype = 0, filter = 0, rx = 1, ry = 1;
     size_t texel_bytes() const { return size_t(padded)*(dtype == SFB_DTYPE_U8 ? 1 : (dtype == SFB_DTYPE_F16 ? 2 : 4)); }
     DevSampler dev() const {
         DevSampler s;
-        s.hw = external ? 0ull : (unsigned long long)obj;
+        s.hw = (external || array_stale) ? 0ull : (unsigned long long)obj;
         s.lin = external ? external : lin;
         s.w = w; s.h = h; s.padded = padded; s.comps = comps; s.dtype = dtype; s.filter = filter; s.rx = rx; s.ry = ry;
         return s;

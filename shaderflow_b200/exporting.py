@@ -1,0 +1,195 @@
+"""ExportingHelper — where finished frames go (API mirror of shaderflow/exporting.py).
+
+The reference reads the GL framebuffer into a ring of mapped buffers and lets turbopipe write them to an
+ffmpeg child (exporting.py:140-174). Here the ring lives in libsfb200 (sfb_pipe_*: device frames +
+pinned host mirrors + a writer thread); the kernels render straight into the ring's device frame.
+Sinks: an ffmpeg child when the binary exists (same rawvideo rgb24 + vflip contract, exporting.py:94-103),
+a raw .rgb file, bytes, or a null sink that still pays the device→host copy."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import tempfile
+import time
+from enum import Enum
+from pathlib import Path
+from typing import TYPE_CHECKING, Any, Callable, Optional
+
+from attrs import Factory, define
+
+from shaderflow_b200 import _native as N
+from shaderflow_b200 import logger
+
+if TYPE_CHECKING:
+    from shaderflow_b200.scene import ShaderScene
+
+
+class OutputType(str, Enum):
+    PATH = "file"
+    PIPE = "pipe"
+    RAW = "raw"
+    NULL = "null"
+    TCP = "tcp"
+
+
+@define
+class ExportingHelper:
+    scene: "ShaderScene"
+    type: Optional[OutputType] = None
+    frame: int = 0
+    start: float = Factory(time.monotonic)
+    relay: Optional[Callable[[int, int], None]] = None
+    bar: Any = None
+    process: Optional[subprocess.Popen] = None
+    stdout: Any = None
+    stderr: Any = None
+    fileno: Optional[int] = None
+    output: Any = None
+    pipe_handle: Optional[N.Pipe] = None
+    buffers: int = 5
+    took: Optional[float] = None
+    _file: Any = None
+    _target: Optional[int] = None
+
+    pipe_output = property(lambda self: self.type is OutputType.PIPE)
+    path_output = property(lambda self: self.type is OutputType.PATH)
+    tcp_output = property(lambda self: self.type is OutputType.TCP)
+
+    @property
+    def total_frames(self) -> int:
+        return max(1, round(self.scene.runtime*self.scene.fps))
+
+    @property
+    def frame_bytes(self) -> int:
+        return self.scene.width*self.scene.height*3
+
+    def open_bar(self) -> None:
+        try:
+            import tqdm
+            quiet = bool(self.relay) or self.scene.realtime or os.environ.get("SHADERFLOW_PROGRESS", "1") == "0"
+            self.bar = tqdm.tqdm(total=self.total_frames, disable=(True if quiet else None), desc=f"Scene ({self.scene.name}) → Video",
+                                 unit=" frames", dynamic_ncols=True, mininterval=1/30, maxinterval=0.5, smoothing=0.1, leave=False)
+        except Exception:
+            self.bar = None
+
+    def update(self) -> None:
+        if self.relay: self.relay(self.frame, self.total_frames)
+        if self.bar: self.bar.update(1)
+        self.frame += 1
+
+    @property
+    def finished(self) -> bool:
+        return self.frame >= self.total_frames
+
+    # -- sink configuration ----------------------------------------------------------------------
+    def ffmpeg_output(self, output) -> None:
+        """Decides the sink from `output` (exporting.py:105-117 plus the sinks that need no ffmpeg)"""
+        if output in ("pipe", "-", bytes):
+            self.type = OutputType.PIPE
+        elif str(output) in ("null", os.devnull):
+            self.type = OutputType.NULL
+        elif "tcp://" in str(output):
+            raise NotImplementedError
+        elif Path(str(output)).suffix.lower() in (".rgb", ".raw", ".rgb24"):
+            self.type = OutputType.RAW
+            self.output = Path(output).expanduser().absolute()
+            self.output.parent.mkdir(parents=True, exist_ok=True)
+        else:
+            self.type = OutputType.PATH
+            self.output = Path(output).expanduser().absolute()
+            self.output.parent.mkdir(parents=True, exist_ok=True)
+
+    def ffmpeg_command(self) -> list[str]:
+        """rawvideo rgb24 frames, bottom row first, on stdin; vflip restores top-down
+        (exporting.py:94-103). Codec selection is ffmpeg's default for the container."""
+        s = self.scene
+        command = [shutil.which("ffmpeg") or "ffmpeg", "-hide_banner", "-loglevel", "error", "-y",
+                   "-f", "rawvideo", "-pix_fmt", "rgb24", "-s", f"{s.width}x{s.height}", "-r", f"{s.fps}", "-i", "-"]
+        for module in s.modules:
+            extra = module.ffhook(self)
+            if extra:
+                command += list(extra)
+        command += ["-vf", "vflip", "-t", f"{s.runtime}"]
+        command += ["-f", "matroska", "-"] if self.pipe_output else [str(self.output)]
+        return command
+
+    def popen(self) -> None:
+        fd = -1
+        if self.type is OutputType.RAW:
+            self._file = open(self.output, "wb")
+            fd = self._file.fileno()
+        elif self.type in (OutputType.PATH, OutputType.PIPE):
+            if not shutil.which("ffmpeg"):
+                if self.type is OutputType.PIPE:     # raw rgb24 bytes instead of an encoded stream
+                    self._file = tempfile.TemporaryFile(mode="w+b")
+                    fd = self._file.fileno()
+                else:
+                    raise RuntimeError(logger.error(
+                        f"No ffmpeg binary on PATH to encode '{self.output}'. Export raw frames with "
+                        "output='frames.rgb', bytes with output='pipe', or discard them with output='null'"))
+            else:
+                self.stderr, self.stdout = tempfile.TemporaryFile(mode="r+b"), tempfile.TemporaryFile(mode="r+b")
+                self.process = subprocess.Popen(self.ffmpeg_command(), stdin=subprocess.PIPE,
+                                                stdout=self.stdout, stderr=self.stderr)
+                fd = self.process.stdin.fileno()
+        self.fileno = fd
+        self.pipe_handle = N.Pipe(self.scene.cuda, fd, max(2, int(self.buffers)), self.frame_bytes)
+
+    def make_buffers(self, n: int = 2) -> None:
+        self.buffers = n
+
+    # -- per frame -------------------------------------------------------------------------------
+    def target(self) -> Optional[int]:
+        """Device pointer the next frame is rendered into (a frame of the sink's ring)"""
+        if self.pipe_handle is None:
+            return None
+        if self._target is None:
+            self._target = self.pipe_handle.acquire()
+        return self._target
+
+    def pipe(self, turbo: bool = True) -> None:
+        """Hands the frame just rendered to the sink (exporting.py:151-174)"""
+        if self.pipe_handle is None:
+            return
+        if self.process is not None and self.process.poll() is not None:
+            self.stderr.seek(0)
+            raise RuntimeError("FFmpeg process closed unexpectedly with traceback:\n" + self.stderr.read().decode("utf-8"))
+        self.pipe_handle.submit(self._target)
+        self._target = None
+        if not turbo:
+            self.pipe_handle.sync()
+
+    def finish(self) -> None:
+        if self.pipe_handle is not None:
+            self.pipe_handle.sync()
+            self.pipe_handle.close()
+            self.pipe_handle = None
+        if self.process is not None:
+            logger.info("Waiting for FFmpeg process to finish encoding")
+            self.process.stdin.close()
+            self.process.wait()
+            self.stdout.seek(0)
+        if self._file is not None and self.type is OutputType.RAW:
+            self._file.close()
+        if self.bar is not None:
+            self.bar.close()
+        self.took = time.monotonic() - self.start
+
+    def result(self):
+        if self.type is OutputType.PIPE:
+            if self.process is not None:
+                return self.stdout.read()
+            self._file.seek(0)
+            data = self._file.read()
+            self._file.close()
+            return data
+        if self.type in (OutputType.PATH, OutputType.RAW):
+            return self.output
+        return None
+
+    def log_stats(self, output) -> None:
+        if self.scene.exporting:
+            logger.info(f"Finished rendering ({output})")
+        logger.info(f"• Stats: (Took {self.took:.2f}s) at ({self.frame/self.took:.2f}fps | "
+                    f"{self.scene.runtime/self.took:.2f}x Realtime) with ({self.frame} Total Frames)")

@@ -1,0 +1,209 @@
+"""ShaderProgram — one fullscreen fragment pass rendering into its own ShaderTexture.
+API mirror of shaderflow/shader.py:98-425. Where the reference assembles GLSL and asks the GL driver to
+compile it (shader.py:190-239,313-349), `compile()` recognises the fragment (registry.py) and selects
+the ahead-of-time CUDA kernel; `render()` packs the module pipeline into one `sfb_uniforms` block and
+launches it (sfb_render_screen / sfb_render_final)."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Iterable, Optional, Union
+
+import numpy as np
+from attrs import Factory, define
+
+from shaderflow_b200 import _native as N
+from shaderflow_b200 import logger, registry
+from shaderflow_b200.message import ShaderMessage
+from shaderflow_b200.module import ShaderModule
+from shaderflow_b200.texture import ShaderTexture, TextureBox
+from shaderflow_b200.variable import FlatVariable, InVariable, OutVariable, ShaderVariable
+
+_FIXED_FIELDS = {name for name, _ in N.Uniforms._fields_} - {"extra"}
+DEFAULT_FRAGMENT = "// sfb200: scene=default"
+FINAL_FRAGMENT = "// sfb200: scene=final"
+
+
+def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[str]) -> N.Uniforms:
+    """name → value table of a pipeline → the POD block; numpy scalars/vectors cast to float32 like
+    GL uniform uploads do"""
+    for name in _FIXED_FIELDS:
+        value = values.get(name)
+        if value is None:
+            continue
+        field = getattr(block, name)
+        if hasattr(field, "__len__"):
+            flat = np.asarray(value, dtype=np.float64).reshape(-1)
+            for i in range(len(field)):
+                field[i] = float(flat[i])
+        elif isinstance(field, int):
+            setattr(block, name, int(value))
+        else:
+            setattr(block, name, float(value))
+    for slot, name in enumerate(extra_names):
+        value = values.get(name)
+        if value is None:
+            raise RuntimeError(f"Uniform '{name}' required by the shader is not in the scene's pipeline")
+        flat = np.asarray(value, dtype=np.float64).reshape(-1)
+        for i in range(min(4, len(flat))):
+            block.extra[slot][i] = float(flat[i])
+    return block
+
+
+@define
+class ShaderProgram(ShaderModule):
+    version: int = 330
+    clear: bool = True
+    instances: int = 1
+    texture: ShaderTexture = None
+
+    vertex_variables: list = Factory(list)
+    fragment_variables: list = Factory(list)
+    vertices: list = Factory(list)
+
+    _vertex: Union[Path, str] = ""
+    _fragment: Union[Path, str] = ""
+
+    scene_id: Optional[int] = None
+    """Index of the ahead-of-time kernel selected by compile() (SFB_SCENE_*)"""
+    scene_info: Optional[dict] = None
+    filter_flags: int = N.FILTER_EXACT
+    """SFB_FILTER_EXACT (parity default) or SFB_FILTER_HARDWARE"""
+
+    def build(self):
+        self.texture = ShaderTexture(scene=self.scene, name=self.name, track=True)
+        # Declarations kept for introspection; the CUDA kernels get varyings from the rasteriser rule
+        self.fragment_variable(OutVariable("vec4", "fragColor"))
+        self.vertex_variable(InVariable("vec2", "vertex_position"))
+        self.vertex_variable(InVariable("vec2", "vertex_gluv"))
+        for name in ("fragCoord", "stxy", "glxy", "stuv", "astuv", "gluv", "agluv"):
+            self.traverse_variable(ShaderVariable("vec2", name))
+        self.traverse_variable(FlatVariable("int", "instance"))
+        for x in (-1, 1):
+            for y in (-1, 1):
+                self.add_vertice(x=x, y=y, u=x, v=y)
+        self._fragment = DEFAULT_FRAGMENT
+
+    # -- declarations (API compatibility) ------------------------------------------------------
+    def vertex_variable(self, variable: ShaderVariable) -> None:
+        if variable not in self.vertex_variables: self.vertex_variables.append(variable)
+
+    def fragment_variable(self, variable: ShaderVariable) -> None:
+        if variable not in self.fragment_variables: self.fragment_variables.append(variable)
+
+    def common_variable(self, variable: ShaderVariable) -> None:
+        self.fragment_variable(variable); self.vertex_variable(variable)
+
+    def traverse_variable(self, variable: ShaderVariable) -> None:
+        self.fragment_variable(variable.copy(direction="in"))
+        self.vertex_variable(variable.copy(direction="out"))
+
+    def add_vertice(self, x: float = 0, y: float = 0, u: float = 0, v: float = 0) -> None:
+        self.vertices.extend((x, y, u, v))
+
+    # -- sources -------------------------------------------------------------------------------
+    @property
+    def vertex(self) -> str:
+        return registry.read(self._vertex)
+
+    @vertex.setter
+    def vertex(self, value: Union[Path, str]):
+        self._vertex = value
+
+    @property
+    def fragment(self) -> str:
+        return registry.read(self._fragment)
+
+    @fragment.setter
+    def fragment(self, value: Union[Path, str]):
+        self._fragment = value
+        self.scene_id = None
+
+    # -- "compilation" -------------------------------------------------------------------------
+    def compile(self) -> "ShaderProgram":
+        if self.texture.final:
+            self.scene_id, self.scene_info = -1, dict(name="final", extra=[], samplers=[])
+            return self
+        name = registry.resolve(self._fragment)
+        if name is None:
+            names = [N.scene_info(i)["name"] for i in range(8)]
+            raise RuntimeError(logger.error(
+                f"ShaderProgram '{self.name}': this fragment shader is not one the CUDA backend has a "
+                f"kernel for (digest {registry.digest(self.fragment)}). Built-in scenes: {names}. "
+                "Add `// sfb200: scene=<name>` to select one explicitly."))
+        self.scene_id = N.scene_lookup(name)
+        self.scene_info = N.scene_info(self.scene_id)
+        return self
+
+    # -- uniforms ------------------------------------------------------------------------------
+    def gather(self, pipeline: Iterable[ShaderVariable]) -> tuple[dict, dict]:
+        """Splits a pipeline into {uniform name: value} and {sampler name: TextureBox}"""
+        values, samplers = {}, {}
+        for variable in pipeline:
+            if variable.type == "sampler2D":
+                samplers[variable.name] = variable.value
+            elif variable.value is not None:
+                values[variable.name] = variable.value
+        for module in self.scene.modules:
+            if isinstance(module, ShaderTexture):
+                for alias, box in module.sampler_names().items():
+                    samplers.setdefault(alias, box)
+        return values, samplers
+
+    def resolve_samplers(self, samplers: dict[str, TextureBox]) -> list:
+        out = []
+        for name in self.scene_info["samplers"]:
+            box = samplers.get(name)
+            if box is None or box.texture is None:
+                raise RuntimeError(f"Shader '{self.name}' samples '{name}' but the scene has no such texture")
+            out.append(box.texture)
+        return out
+
+    def uniform_block(self, values: dict) -> N.Uniforms:
+        w, h = self.scene.resolution
+        block = N.Uniforms.defaults(w, h)
+        return pack_uniforms(block, values, self.scene_info["extra"])
+
+    def set_uniform(self, name: str, value: Any = None) -> None:
+        if self.scene_id is None:
+            raise RuntimeError("Shader hasn't been compiled yet")
+
+    # -- rendering -----------------------------------------------------------------------------
+    def render(self, target: Optional[int] = None) -> None:
+        """target: device pointer for the final pass output (defaults to the scene's frame buffer)"""
+        if self.scene_id is None:
+            raise RuntimeError("Shader hasn't been compiled yet")
+        cuda, scene = self.scene.cuda, self.scene
+        if self.texture.final:
+            # shader.py:391-396: only iScreen's texture, iResolution and iSubsample
+            source = scene.shader.texture
+            sw, sh = source.size
+            pointer, _ = source.get_box().texture.storage()
+            cuda.render_final(pointer, sw, sh, scene.width, scene.height, scene.subsample, 3,
+                              target if target is not None else scene.frame_pointer)
+            return
+        values, samplers = self.gather(self.full_pipeline())
+        textures = self.resolve_samplers(samplers)
+        w, h = self.texture.size
+        for layer, box in enumerate(self.texture.row(0)):
+            values["iLayer"] = layer
+            block = self.uniform_block(values)
+            pointer, _ = box.texture.storage()
+            cuda.render_screen(self.scene_id, block, textures, w, h, pointer, None, self.filter_flags)
+        self.texture.roll()
+
+    def render_fused(self, target: int, ssaa: int) -> None:
+        """K3+K4 in one launch straight into `target` (rgb24): iScreen never exists in HBM"""
+        values, samplers = self.gather(self.full_pipeline())
+        values["iLayer"] = 0
+        scene = self.scene
+        scene.cuda.render_frame(self.scene_id, self.uniform_block(values), self.resolve_samplers(samplers),
+                                scene.width, scene.height, ssaa, scene.subsample, 3, target, self.filter_flags)
+
+    def update(self) -> None:
+        self.render()
+
+    def handle(self, message) -> None:
+        if isinstance(message, ShaderMessage.Shader.Compile):
+            self.compile()
+        elif isinstance(message, ShaderMessage.Shader.Render):
+            self.render()

@@ -1,0 +1,60 @@
+"""Frame sharding and the reassembly exchange on CPU: world_size-2 (and 3) gloo process groups."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from shaderflow_b200.distributed import FrameGather, max_over_ranks, owner_of, shard_range
+
+
+def test_shard_ranges_partition_the_export():
+    for n in (0, 1, 7, 60, 3600, 3601):
+        for world in (1, 2, 3, 8):
+            ranges = [shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+            for f in range(0, n, max(1, n//17)):
+                r = owner_of(f, n, world)
+                assert ranges[r][0] <= f < ranges[r][1]
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank: int, world: int, port: int, n_frames: int, chunk: int, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_range(n_frames, rank, world)
+    # frame k is filled with (k mod 251) and stamped with its index
+    local = torch.stack([torch.full((4, 6, 3), k % 251, dtype=torch.uint8) for k in range(a, b)]) if b > a \
+        else torch.empty((0, 4, 6, 3), dtype=torch.uint8)
+    got = [blk.clone() for blk in FrameGather(n_frames, rank, world, chunk=chunk).stream(local)]
+    slowest = max_over_ranks(float(rank + 1))
+    if rank == 0:
+        frames = torch.cat(got) if got else torch.empty((0, 4, 6, 3), dtype=torch.uint8)
+        out.put((frames.numpy(), slowest))
+    else:
+        assert got == [] and slowest == float(world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames,chunk", [(2, 21, 4), (2, 8, 16), (3, 10, 3)])
+def test_gather_reassembles_frames_in_time_order(world, n_frames, chunk):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, chunk, out)) for r in range(world)]
+    for p in procs: p.start()
+    frames, slowest = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert frames.shape == (n_frames, 4, 6, 3) and slowest == float(world)
+    assert np.array_equal(frames[:, 0, 0, 0], np.arange(n_frames) % 251)

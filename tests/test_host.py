@@ -1,0 +1,167 @@
+"""Host-side logic of the drop-in layer (no GPU): the reference's own Resolution.fit tests ported
+(resolution.py:90-116), scheduler/scene clock against the goldens, module graph order, uniform packing,
+the GLSL registry, host DynamicNumber against the reference goldens."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import audio_np as A
+from shaderflow_b200 import _native as N
+from shaderflow_b200 import registry
+from shaderflow_b200.dynamics import DynamicNumber
+from shaderflow_b200.resolution import Resolution
+from shaderflow_b200.scheduler import Scheduler
+from shaderflow_b200.shader import pack_uniforms
+
+
+class TestResolutionFit:
+    """Ports of the reference's inline `class __pytest__` (resolution.py:90-116)"""
+    def test_keep_nothing(self):
+        assert Resolution.fit(old=(1920, 1080)) == (1920, 1080)
+
+    def test_override_components(self):
+        assert Resolution.fit(old=(1920, 1080), new=(1280, None)) == (1280, 1080)
+        assert Resolution.fit(old=(1920, 1080), new=(None, 720)) == (1920, 720)
+
+    def test_missing_components(self):
+        with pytest.raises(ValueError):
+            Resolution.fit(old=(1920, None), new=(1280, None))
+        with pytest.raises(ValueError):
+            Resolution.fit(old=(None, 1080), new=(None, None))
+
+    def test_aspect_ratio(self):
+        assert Resolution.fit(old=(1920, 1080), new=(1280, None), ar=16/9) == (1280, 720)
+        assert Resolution.fit(old=(1920, 1080), new=(None, 720), ar=16/9) == (1280, 720)
+        assert Resolution.fit(old=(1920, 1080), new=(1000, None), ar=2.0) == (1000, 500)
+        assert Resolution.fit(old=(1920, 1080), new=(None, 500), ar=2.0) == (1000, 500)
+
+    def test_aspect_ratio_prioritize_width(self):
+        assert Resolution.fit(old=(1920, 1080), new=(1000, 720), ar=2) == (1000, 500)
+
+    def test_limit_maximum_resolution(self):
+        assert Resolution.fit(old=(3840, 2160), new=(3800, 2100), max=(1920, 1080)) == (1920, 1080)
+        assert Resolution.fit(old=(3000, 3000), new=(2000, 2000), max=(6000, 720), ar=16/9) == (1280, 720)
+
+    def test_against_reference_outputs(self, golden_dir):
+        for row in json.loads((golden_dir/"resolution_fit.json").read_text()):
+            kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in row["kwargs"].items()}
+            assert list(Resolution.fit(**kw)) == row["result"]
+
+
+def test_scheduler_freewheel_clock_matches_golden(golden_dir):
+    """Driving the mirrored Scheduler the way ShaderScene.main does reproduces the reference's
+    per-frame time/dt (goldens were produced by the reference's own SchedulerTask)"""
+    gold = np.load(golden_dir/"audio_chirp_1000.npz")
+    state = dict(time=0.0, dt=0.0, seen=[])
+    def step(dt=0.0):
+        state["seen"].append((state["time"], state["dt"]))
+        state["dt"] = dt*1.0
+        state["time"] += state["dt"]
+    sched = Scheduler()
+    task = sched.new(task=step, frequency=24.0, freewheel=True, precise=True)
+    for _ in range(len(gold["time"])):
+        assert sched.next() is task
+    assert np.array_equal([t for t, _ in state["seen"]], gold["time"])
+    assert np.array_equal([d for _, d in state["seen"]], gold["dt"])
+
+
+def test_dry_scene_graph_and_pipeline():
+    """Module creation order and uniform names are what the reference's metaprogramming would
+    declare (scene.py:128-195, camera.py:146-201, audio/module.py:413-421)"""
+    import examples.demo as demo
+    scene = demo.Visualizer(backend="dry")
+    scene.initialize()
+    kinds = [type(m).__name__ for m in scene.modules]
+    assert kinds[:4] == ["Visualizer", "ShaderFrametimer", "ShaderKeyboard", "ShaderCamera"]
+    assert kinds[4:13] == ["ShaderDynamics"]*9
+    assert [m.name for m in scene.modules[4:13]] == ["iCameraPosition", "iCameraSeparation", "iCameraRotation",
+        "iCameraZenith", "iCameraZoom", "iCameraIsometric", "iCameraFocalLength", "iCameraOrbital", "iCameraDolly"]
+    assert kinds[13:17] == ["ShaderProgram", "ShaderTexture", "ShaderProgram", "ShaderTexture"]
+    assert kinds[17:] == ["ShaderAudio", "ShaderDynamics", "ShaderDynamics", "ShaderWaveform", "ShaderTexture",
+                          "ShaderSpectrogram", "ShaderTexture", "ShaderTexture"]
+    names = [v.name for v in scene.full_pipeline()]
+    for required in ("iTime", "iResolution", "iCameraPosition", "iCameraZoom", "iAudioVolume", "iAudioVolumeIntegral",
+                     "iAudioSTD", "iSpectrogramBins", "iWaveformLength", "backgroundSize", "background0x0", "iScreen0x0"):
+        assert required in names
+    assert "iCameraRotation" not in names                      # primary=False (camera.py:155-159)
+    assert scene.spectrogram.spectrogram_bins == 115
+    assert scene.spectrogram.texture.repeat_y is False and scene.waveform.texture.repeat_x is False
+    assert scene.waveform.chunk_size == 735 and scene.waveform._points == 180
+    # texture aliases of texture.py:354-368
+    assert set(scene.back.sampler_names()) == {"background0x0", "background"}
+    scene.shader.compile()
+    assert scene.shader.scene_info["name"] == "visualizer"
+    values, samplers = scene.shader.gather(scene.full_pipeline())
+    block = scene.shader.uniform_block(values)
+    assert tuple(block.iResolution) == (1920.0, 1080.0) and block.iCameraMode == 1 and block.iCameraZoom == 1.0
+    assert tuple(block.iCameraForward) == (0.0, 0.0, 1.0) and abs(block.iQuality - 0.5) < 1e-7
+    assert {"background", "iSpectrogram", "iWaveform"} <= set(samplers)
+
+
+def test_dry_main_steps_time_like_the_reference():
+    import examples.demo as demo
+    scene = demo.ShaderToy(backend="dry")
+    seen = []
+    orig = scene.next
+    scene.main(width=64, height=36, fps=24.0, time=1.25)
+    time, dt, _ = A.frame_clock(30, 24.0)
+    assert scene.frame_index == 30 and scene.total_frames == 30
+    assert abs(scene.time - (time[-1] + 1/24)) < 1e-12
+    assert scene.resolution == (64, 36) and scene.render_resolution == (64, 36)
+    scene.ssaa = 2
+    assert scene.render_resolution == (128, 72) and scene.fusable == 2
+    scene.subsample = 3
+    assert scene.fusable is None
+
+
+def test_pack_uniforms_casts_and_reports_missing():
+    block = pack_uniforms(N.Uniforms.defaults(64, 32), dict(iTime=np.float64(1/3), iResolution=(64, 32), iFrame=7,
+        iCameraPosition=np.array([1, 2, 3.0]), iAudioVolume=np.array(0.25)), ["iAudioVolume"])
+    assert block.iTime == np.float32(1/3) and block.iFrame == 7 and tuple(block.iCameraPosition) == (1.0, 2.0, 3.0)
+    assert block.extra[0][0] == 0.25
+    with pytest.raises(RuntimeError, match="iAudioSTD"):
+        pack_uniforms(N.Uniforms.defaults(64, 32), {}, ["iAudioSTD"])
+
+
+def test_registry_directive_and_normalisation():
+    assert registry.resolve("// sfb200: scene=mandelbrot\nvoid main(){}") == "mandelbrot"
+    a = "void main() {\n  fragColor = vec4(1.0); // white\n}"
+    b = "/* header */ void main(){fragColor=vec4(1.0);}"
+    assert registry.digest(a) == registry.digest(b)
+    assert registry.resolve(a) is None
+    assert len(registry.KNOWN_HASHES) == 8
+
+
+@pytest.mark.reference
+def test_registry_hashes_match_reference_tree():
+    from pathlib import Path
+    ref = Path("/root/reference")
+    if not ref.exists():
+        pytest.skip("no /root/reference here")
+    for rel, name in (("examples/basic/shaders/visualizer.frag", "visualizer"), ("examples/basic/shaders/bars.frag", "bars"),
+                      ("examples/fractals/shaders/mandelbrot.frag", "mandelbrot"),
+                      ("shaderflow/resources/shaders/fragment/default.glsl", "default")):
+        assert registry.resolve(ref/rel) == name
+
+
+def test_host_dynamics_matches_reference_golden(golden_dir):
+    """The host DynamicNumber (camera, user knobs) against the reference's volume/std recurrences"""
+    gold = np.load(golden_dir/"audio_noise.npz")
+    vol = DynamicNumber(frequency=2, zeta=1, response=0, value=0, integrate=True)
+    std = DynamicNumber(frequency=10, zeta=1, response=0, value=0)
+    for k in range(len(gold["dt"])):
+        vol.target = np.float32(gold["vol_target"][k]); std.target = np.float32(gold["std_target"][k])
+        vol.next(dt=abs(gold["dt"][k])); std.next(dt=abs(gold["dt"][k]))
+        assert vol.value == gold["volume"][k] and vol.integral == gold["volume_integral"][k] and std.value == gold["std"][k]
+
+
+def test_camera_basis_and_scripted_rotation():
+    import examples.demo as demo
+    scene = demo.Basic(backend="dry"); scene.initialize()
+    cam = scene.camera
+    assert np.allclose(cam.right, (1, 0, 0)) and np.allclose(cam.up, (0, 1, 0)) and np.allclose(cam.forward, (0, 0, 1))
+    cam.rotate((0, 1, 0), 90)
+    cam.rotation.value = cam.rotation.target
+    assert np.allclose(cam.forward, (1, 0, 0), atol=1e-12) and np.allclose(cam.right, (0, 0, -1), atol=1e-12)
+    assert abs(cam.fov - 90.0) < 1e-9
