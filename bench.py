@@ -1,0 +1,259 @@
+"""
+bench.py — BASELINE.json's headline metric on B200: frames/s of the 4K (3840x2160) 2xSSAA music-visualizer
+export, frame-sharded over N GPUs of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one export of a clip of N seconds through the public API (`ShaderScene.main`): every rank shades
+`--frames-per-step` (60) frames of its contiguous time range with the fused visualizer kernel after the
+STFT/audio-track kernels ran for the clip, and rank 0 reassembles the frames (weak scaling: per-GPU work
+is fixed). Two timed passes share that step:
+  value : inputs (PCM clip, background texture) already resident in HBM, frames stay in HBM;
+  e2e   : the clip comes from pinned HOST memory each step (H2D inside the timed region) and every frame
+          goes through the sink ring to pinned HOST memory (D2H inside the timed region, null sink).
+Timing: CUDA events on the launch stream around each step, barrier + synchronize on both sides, max over
+ranks. The oracle (numpy port of the reference path) is only ever the CPU baseline here, never the product.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = ("examples/basic Visualizer, 3840x2160, ssaa=2 (7680x4320 shaded fragments/frame), subsample=2, 60 fps, "
+            "synthetic log-chirp 20 Hz-20 kHz (R = reversed L), synthetic 1920x1080 background; BASELINE.json configs[2]")
+METRIC = "4K@2xSSAA music-visualizer frames/sec"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--frames-per-step", type=int, default=60, help="frames each rank shades per step")
+    p.add_argument("--width", type=int, default=3840)
+    p.add_argument("--height", type=int, default=2160)
+    p.add_argument("--ssaa", type=int, default=2)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--hardware-filter", action="store_true", help="SFB_FILTER_HARDWARE instead of the exact sampler")
+    return p.parse_args()
+
+
+# -------------------------------------------------------------------------------------------------- #
+# Clock sampling during the timed region (B200_PROFILING.md)
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try: self.proc.wait(timeout=5)
+        except Exception: self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in Path(self.path).read_text().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            loaded = sorted(sm)[len(sm)//4:] if len(sm) > 4 else sm       # drop the idle tail
+            out.update(sm_mhz=float(np.median(loaded)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# -------------------------------------------------------------------------------------------------- #
+# CPU arm (oracle port on the host cores)
+
+def cpu_sample(args) -> dict:
+    from oracle import cpu_bench
+    r = cpu_bench.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa, rows_per_band=8, bands_per_worker=6)
+    return dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+
+
+def run_reference(args, rank: int) -> None:
+    """--impl reference: the reference's CPU implementation of the path. The real reference (llvmpipe +
+    moderngl + numpy) cannot be installed here or on the GPU box (no GL stack), so this is the
+    oracle port on all host cores; each step is a bounded sample of one 4K 2xSSAA frame."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    values, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_bench.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa,
+                                           rows_per_band=4, bands_per_worker=2)
+        if i >= args.warmup:
+            values.append(last["frames_per_s"])
+    value = float(np.mean(values)) if values else last["frames_per_s"]
+    line = dict(impl="reference", metric=METRIC, value=value, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3/value, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", gpu_launches=0,
+                config=dict(workload=WORKLOAD, step="bounded sample of one frame: row bands shaded on every host core, extrapolated"),
+                cpu_baseline=dict(value=value, unit="frames/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------- #
+# B200 arm
+
+def run_b200(args, rank: int, world: int, local: int) -> None:
+    import torch
+    import torch.distributed as dist
+    from oracle import audio_np as A               # synthetic inputs only (synth_chirp); never the compute path
+    from shaderflow_b200 import _native as N
+    from shaderflow_b200 import distributed as D
+    from examples.demo import Visualizer, synthetic_background
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        D.init_process_group("nccl")
+    F, W, H, S = args.frames_per_step, args.width, args.height, args.ssaa
+    fps = 60.0
+    total_frames = F*world
+    seconds = total_frames/fps
+    clip = A.synth_chirp(seconds)
+    pinned = torch.from_numpy(clip).pin_memory()
+
+    Visualizer.background = synthetic_background(1920, 1080)
+    scene = Visualizer(device=local)
+    scene.initialize()
+    if args.hardware_filter:
+        scene.shader.filter_flags = N.FILTER_HARDWARE
+    scene.audio.load(clip, 44100)
+    scene.audio.device_clip(local)                 # resident before any timed region
+    flags = dict(width=W, height=H, ssaa=S, subsample=2, fps=fps, time=seconds)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn) -> float:
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        barrier()
+        return D.max_over_ranks(ms) if world > 1 else ms
+
+    def step_value():
+        scene.main(output=None, **flags)
+
+    def step_e2e():
+        scene.audio.load(pinned.numpy(), 44100)    # drops the device copy: the clip is uploaded again from pinned memory
+        scene.main(output="null", buffers=4, **flags)
+
+    for _ in range(args.warmup):
+        timed(step_value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    scene.kernel_events = []
+    launches0 = scene.cuda.launches
+    value_ms = [timed(step_value) for _ in range(args.steps)]
+    launches = scene.cuda.launches - launches0
+    kernel_events, scene.kernel_events = scene.kernel_events, None
+    torch.cuda.synchronize()
+    kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
+    clocks = sampler.stop() if rank == 0 else {}
+
+    for _ in range(min(args.warmup, 2)):
+        timed(step_e2e)
+    e2e_ms = [timed(step_e2e) for _ in range(args.steps)]
+
+    if rank != 0:
+        return
+    ms_per_step = float(np.mean(value_ms))
+    value = total_frames/(ms_per_step/1e3)
+    e2e_value = total_frames/(float(np.mean(e2e_ms))/1e3)
+
+    peaks = {}
+    try: peaks = json.loads((ROOT/"MEASURED_PEAKS.json").read_text())
+    except Exception: pass
+    peak, peak_kind = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    # Algorithmic bytes of one fused visualizer launch: rgb24 store + each texture read once
+    algorithmic = W*H*3 + 1920*1080*4 + 115*2*4 + 180*2*4
+    kernel_avg_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
+    achieved = algorithmic/(kernel_avg_ms/1e3)/1e9
+    traffic = None
+    try: traffic = json.loads((ROOT/"profiles"/"ncu_summary.json").read_text())["frame_kernel_visualizer"]["dram_bytes_per_launch"]
+    except Exception: pass
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved/peak, traffic=traffic,
+                    kernel="frame_kernel<SFB_SCENE_VISUALIZER>", kernel_ms=kernel_avg_ms, launches_timed=len(kernel_ms),
+                    algorithmic_bytes_per_launch=algorithmic, peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                    note="the kernel is texture/ALU-bound (91 bilinear taps per fragment); fragments/s is the meaningful rate",
+                    gfragments_per_s=W*S*H*S/(kernel_avg_ms/1e3)/1e9)
+
+    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=WORKLOAD, frames_per_step_per_gpu=F, global_frames_per_step=total_frames,
+                            parallelism=f"frame-shard x{world} + gather to rank 0" if world > 1 else "single GPU",
+                            filter="hardware" if args.hardware_filter else "exact",
+                            l2="each step streams %.2f GB of frames per GPU (>> 126 MB L2); the 8.3 MB background is reused "
+                               "across frames by design" % (F*W*H*3/1e9)),
+                clocks=dict(sm_mhz=clocks.get("sm_mhz"), sm_max_mhz=clocks.get("sm_max_mhz"), reasons=clocks.get("reasons", [])),
+                e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(clip.nbytes),
+                         d2h_bytes_per_step=int(total_frames*W*H*3), ms_per_step=float(np.mean(e2e_ms))),
+                gpu_launches=int(launches), roofline=roofline)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sample(args)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves the way the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

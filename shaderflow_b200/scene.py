@@ -64,6 +64,8 @@ class ShaderScene(ShaderModule):
     cli: Any = Factory(_Cli)
     fuse: bool = True
     """Use the fused K3+K4 kernel whenever final.glsl degenerates to a box filter"""
+    kernel_events: Any = None
+    """When a list: (start, end) torch CUDA events are appended around every shading launch (bench.py)"""
 
     # -- lifecycle -------------------------------------------------------------------------------
     def __attrs_post_init__(self) -> None:

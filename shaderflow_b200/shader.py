@@ -196,8 +196,17 @@ class ShaderProgram(ShaderModule):
         values, samplers = self.gather(self.full_pipeline())
         values["iLayer"] = 0
         scene = self.scene
-        scene.cuda.render_frame(self.scene_id, self.uniform_block(values), self.resolve_samplers(samplers),
-                                scene.width, scene.height, ssaa, scene.subsample, 3, target, self.filter_flags)
+        block, textures = self.uniform_block(values), self.resolve_samplers(samplers)
+        events = scene.kernel_events
+        if events is not None:
+            import torch
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+        scene.cuda.render_frame(self.scene_id, block, textures, scene.width, scene.height, ssaa,
+                                scene.subsample, 3, target, self.filter_flags)
+        if events is not None:
+            end.record()
+            events.append((start, end))
 
     def update(self) -> None:
         self.render()
