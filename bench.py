@@ -103,7 +103,7 @@ class ClockSampler:
 
 def cpu_sample(args) -> dict:
     from oracle import cpu_bench
-    r = cpu_bench.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa, rows_per_band=8, bands_per_worker=6)
+    r = cpu_bench.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa, rows_per_band=8, bands_per_worker=3)
     return dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
 
 

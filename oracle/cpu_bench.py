@@ -53,12 +53,31 @@ def _band(args) -> int:
     return out.shape[0]*out.shape[1]
 
 
+def usable_cores() -> int:
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            text = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if text[0] != "max":
+                    n = min(n, max(1, int(int(text[0])/int(text[1]))))
+            else:
+                quota = int(text[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota//period))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def visualizer_sample(width: int = 3840, height: int = 2160, ssaa: int = 2, rows_per_band: int = 4,
                       bands_per_worker: int = 3, workers: int | None = None, bg_size=(1920, 1080), seed: int = 1) -> dict:
     """Shades `workers*bands_per_worker` bands of `rows_per_band` fragment rows on `workers` processes.
     → dict(frames_per_s, fragments, seconds, cores, sample)"""
     import multiprocessing as mp
-    workers = workers or (os.cpu_count() or 1)
+    workers = workers or usable_cores()
     Hr = height*ssaa
     n_bands = workers*bands_per_worker
     stride = max(rows_per_band, (Hr - rows_per_band)//max(1, n_bands - 1))
