@@ -136,7 +136,7 @@ def run_reference(args, rank: int) -> None:
 def run_b200(args, rank: int, world: int, local: int) -> None:
     import torch
     import torch.distributed as dist
-    from oracle import audio_np as A               # synthetic inputs only (synth_chirp); never the compute path
+    from shaderflow_b200 import synthetic
     from shaderflow_b200 import _native as N
     from shaderflow_b200 import distributed as D
     from examples.demo import Visualizer, synthetic_background
@@ -148,7 +148,7 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     fps = 60.0
     total_frames = F*world
     seconds = total_frames/fps
-    clip = A.synth_chirp(seconds)
+    clip = synthetic.chirp(seconds)
     pinned = torch.from_numpy(clip).pin_memory()
 
     Visualizer.background = synthetic_background(1920, 1080)

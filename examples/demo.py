@@ -23,15 +23,9 @@ shaders: Path = (Path(__file__).parent/"shaders")
 
 
 def synthetic_background(width: int = 1920, height: int = 1080, seed: int = 1) -> np.ndarray:
-    """Deterministic stand-in for the downloaded wallpaper: smooth colour field + grain, RGB8, top row first"""
-    rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:height, 0:width].astype(np.float64)
-    x /= width; y /= height
-    img = np.stack([0.5 + 0.5*np.sin(6.0*x + 2.0*np.cos(5.0*y)),
-                    0.5 + 0.5*np.sin(4.0*y + 3.0*x*x + 1.0),
-                    0.5 + 0.5*np.cos(9.0*(x - 0.5)*(y - 0.5) + 2.0)], -1)
-    img += rng.uniform(-0.08, 0.08, img.shape)
-    return (np.clip(img, 0, 1)*255).round().astype(np.uint8)
+    """Deterministic stand-in for the downloaded wallpaper (RGB8, top row first)"""
+    from shaderflow_b200 import synthetic
+    return synthetic.background(width, height, seed)
 
 
 class Basic(ShaderScene):

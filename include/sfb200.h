@@ -192,6 +192,8 @@ int sfb_scene_info_get(int scene, sfb_scene_info* info);
 enum {
     SFB_FILTER_EXACT = 0,      /* float32 bilinear on point-fetched texels (parity default)           */
     SFB_FILTER_HARDWARE = 1,   /* cudaTextureObject filtering (9-bit weights, like GL hardware)       */
+    SFB_RENDER_LITERAL = 2,    /* force the literal transliteration of the GLSL (no scene-specific fast  */
+                               /* path); the parity anchor the optimised kernels are compared against   */
 };
 
 /* iScreen pass (K3): one thread per fragment of a target_w x target_h RGBA8 target — replaces

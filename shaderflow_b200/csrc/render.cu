@@ -183,8 +183,31 @@ extern "C" int sfb_scene_info_get(int scene, sfb_scene_info* info) {
 // ------------------------------------------------------------------------------------------------
 // Launchers
 
+// visualizer.frag:26-27 evaluated in strict float32 on the host: 9 angles x 10 walks, stored as
+// dir*walk (the float counters make it 9 directions, not 8)
+static int build_blur_table() {
+    static bool done[64] = {};
+    int device = 0;
+    SFB_CUDA(cudaGetDevice(&device));
+    if (device < 64 && done[device]) return SFB_OK;
+    BlurTable table;
+    const volatile float TAU_F = 6.2831853071795864f, directions = 8.0f, quality = 10.0f;
+    int n = 0;
+    for (volatile float angle = 0.0f; angle < TAU_F; angle = angle + TAU_F/directions) {
+        const float c = cosf(angle), s = sinf(angle);
+        for (volatile float walk = 1.0f/quality; walk <= 1.001f; walk = walk + 1.0f/quality) {
+            if (n >= 90) SFB_FAIL(SFB_ESTATE, "blur table overflow: float loop semantics changed");
+            table.tap[n++] = make_float2(c*walk, s*walk);
+        }
+    }
+    if (n != 90) SFB_FAIL(SFB_ESTATE, "blur table has %d taps, expected 90", n);
+    SFB_CUDA(cudaMemcpyToSymbol(c_blur, &table, sizeof(table)));
+    if (device < 64) done[device] = true;
+    return SFB_OK;
+}
+
 static int fill_params(RenderParams& P, const char* who, int scene, const sfb_uniforms* uniforms,
-                       sfb_tex* const* samplers, int n_samplers) {
+                       sfb_tex* const* samplers, int n_samplers, int flags) {
     SFB_REQUIRE(scene >= 0 && scene < SFB_SCENE_COUNT, "%s: bad scene %d", who, scene);
     SFB_REQUIRE(uniforms, "%s: null uniforms", who);
     SFB_REQUIRE(n_samplers >= SCENES[scene].n_samplers && n_samplers <= SFB_MAX_SAMPLERS,
@@ -194,6 +217,15 @@ static int fill_params(RenderParams& P, const char* who, int scene, const sfb_un
         SFB_REQUIRE(samplers && samplers[i], "%s: sampler %d is null", who, i);
         P.tex[i] = samplers[i]->dev();
         SFB_REQUIRE(P.tex[i].lin, "%s: sampler %d has no storage", who, i);
+    }
+    P.fast = 0;
+    if (scene == SFB_SCENE_VISUALIZER && !(flags & SFB_RENDER_LITERAL)) {
+        const DevSampler& bg = P.tex[0];
+        if (bg.dtype == SFB_DTYPE_U8 && bg.padded == 4 && bg.filter == SFB_FILTER_LINEAR && bg.w >= 2 && bg.h >= 2
+            && bg.w < (1 << 21) && bg.h < (1 << 21)) {
+            if (int e = build_blur_table()) return e;
+            P.fast = 1;
+        }
     }
     return SFB_OK;
 }
@@ -228,7 +260,7 @@ extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     SFB_REQUIRE(ctx && dst_rgba8_dev, "sfb_render_screen: null ctx or destination");
     SFB_REQUIRE(target_w > 0 && target_h > 0, "sfb_render_screen: bad target %dx%d", target_w, target_h);
     RenderParams P{};
-    if (int e = fill_params(P, "sfb_render_screen", scene, uniforms, samplers, n_samplers)) return e;
+    if (int e = fill_params(P, "sfb_render_screen", scene, uniforms, samplers, n_samplers, flags)) return e;
     P.Wr = target_w; P.Hr = target_h;
     P.W = int(uniforms->iResolution[0]); P.H = int(uniforms->iResolution[1]);
     P.inv_Wr = 1.0/double(target_w); P.inv_Hr = 1.0/double(target_h);
@@ -263,7 +295,7 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
         "(got ssaa=%d subsample=%d); use sfb_render_screen + sfb_render_final", ssaa, subsample);
     SFB_REQUIRE(components == 3 || components == 4, "sfb_render_frame: components must be 3 or 4");
     RenderParams P{};
-    if (int e = fill_params(P, "sfb_render_frame", scene, uniforms, samplers, n_samplers)) return e;
+    if (int e = fill_params(P, "sfb_render_frame", scene, uniforms, samplers, n_samplers, flags)) return e;
     P.W = width; P.H = height; P.ssaa = ssaa; P.subsample = subsample; P.comps = components;
     P.Wr = width*ssaa; P.Hr = height*ssaa;
     P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);

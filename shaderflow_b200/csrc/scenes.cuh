@@ -17,6 +17,7 @@ struct RenderParams {
     double inv_Wr, inv_Hr;   // 1/Wr, 1/Hr
     unsigned char* dst;
     float* dst_f32;
+    int fast;                // scene-specific fast path allowed (set by the launcher after checking formats)
 };
 
 struct Frag { vec2 agluv, gluv, astuv, stuv, stxy, glxy; };
@@ -274,11 +275,130 @@ SFB_DEV vec4 scene_raymarch(const RenderParams& P, const Frag& f) {
     return mk4(mk3(1.0f - sqrtf(float(steps))*0.1f), 1.0f);
 }
 
+// ------------------------------------------------------------------------------------------------
+// visualizer.frag, production path. Same mathematics as scene_visualizer (the literal transliteration
+// above stays as the parity anchor and serves SFB_FILTER_HARDWARE / unusual texture formats); what
+// changes is how the 91 bilinear taps of the blur loop (visualizer.frag:19-33) are evaluated:
+//   * the (angle, walk) pairs of the two strict-float32 loops are a 90-entry constant table
+//     (dir*walk), built on the host with the same float arithmetic (render.cu: build_blur_table);
+//   * stexture() on the RGBA8 background is specialised: no integer modulo unless the 2x2 footprint
+//     touches the texture edge, floor via the 1.5*2^23 trick, bytes widened with PRMT + FADD instead of
+//     I2F, the 1/255 of the unorm decode applied once to the tap sum;
+//   * consecutive taps along a walk usually land in the same texel quad: the unpacked quad is kept in
+//     registers and refetched only when (i0, j0) changes.
+// Differences to the literal path are float32 re-association only (~1e-7 relative).
+
+struct BlurTable { float2 tap[90]; };
+__constant__ BlurTable c_blur;
+
+struct QuadSampler {
+    const uchar4* texels; int w, h; int rx, ry;
+    float fw, fh, hw;
+    int qi, qj;
+    vec3 t00, t10, t01, t11;
+
+    SFB_DEV void init(const DevSampler& s) {
+        texels = reinterpret_cast<const uchar4*>(s.lin); w = s.w; h = s.h; rx = s.rx; ry = s.ry;
+        fw = float(s.w); fh = float(s.h); hw = float(s.h)/float(s.w);
+        qi = qj = 0x7fffffff;
+    }
+    static SFB_DEV vec3 widen(uchar4 c) {
+        const unsigned int word = (unsigned int)c.x | ((unsigned int)c.y << 8) | ((unsigned int)c.z << 16) | ((unsigned int)c.w << 24);
+        // byte k into the mantissa of 2^23: float = 8388608 + byte
+        return mk3(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.0f,
+                   __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.0f,
+                   __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.0f);
+    }
+    SFB_DEV void fetch(int i0, int j0) {
+        int i1 = i0 + 1, j1 = j0 + 1;
+        if ((unsigned int)i0 >= (unsigned int)(w - 1) || (unsigned int)j0 >= (unsigned int)(h - 1)) {
+            i0 = wrap_index(i0, w, rx); i1 = wrap_index(i1, w, rx);
+            j0 = wrap_index(j0, h, ry); j1 = wrap_index(j1, h, ry);
+        }
+        const uchar4* r0 = texels + size_t(j0)*size_t(w);
+        const uchar4* r1 = texels + size_t(j1)*size_t(w);
+        t00 = widen(__ldg(r0 + i0)); t10 = widen(__ldg(r0 + i1));
+        t01 = widen(__ldg(r1 + i0)); t11 = widen(__ldg(r1 + i1));
+    }
+    // stexture(image, st) in byte units (0..255); shaderflow.glsl:165-169,202-204 + GL bilinear
+    SFB_DEV vec3 stexture255(vec2 st) {
+        const float ux = ((st.x*2.0f - 1.0f)*hw + 1.0f)/2.0f;
+        const float uy = ((st.y*2.0f - 1.0f) + 1.0f)/2.0f;
+        const float ub = ux*fw - 0.5f, vb = uy*fh - 0.5f;
+        // floor for |x| < 2^22: round to nearest through the magic constant, step down if it went up
+        const float MAGIC = 12582912.0f;
+        float mx = ub + MAGIC, my = vb + MAGIC;
+        float fx = mx - MAGIC, fy = my - MAGIC;
+        if (fx > ub) { fx -= 1.0f; mx -= 1.0f; }
+        if (fy > vb) { fy -= 1.0f; my -= 1.0f; }
+        const int i0 = __float_as_int(mx) - 0x4B400000, j0 = __float_as_int(my) - 0x4B400000;
+        const float a = ub - fx, b = vb - fy;
+        if (i0 != qi || j0 != qj) { fetch(i0, j0); qi = i0; qj = j0; }
+        const vec3 top = t00*(1.0f - a) + t10*a;
+        const vec3 bot = t01*(1.0f - a) + t11*a;
+        return top*(1.0f - b) + bot*b;
+    }
+};
+
+SFB_DEV vec4 scene_visualizer_fast(const RenderParams& P, const Frag& f) {
+    const float iTime = P.u.iTime, iAudioVolume = P.u.extra[0][0], iAudioSTD = P.u.extra[1][0];
+    Camera cam = get_camera(P.u, f);
+    vec2 uv = cam.gluv;
+    vec3 space = mk3(1.0f, 11.0f, 26.0f)/255.0f;
+    if (cam.out_of_bounds) return mk4(space, 0.0f);
+
+    vec2 background_uv = zoom(gluv2stuv(uv), 0.95f + 0.01f*sinf(iTime) - 0.02f*iAudioVolume - 0.03f, mk2(0.5f));
+    background_uv = background_uv + 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
+    QuadSampler bg; bg.init(P.tex[0]);
+    vec3 sum = bg.stexture255(background_uv);
+    {
+        const float intensity = 0.01f*clamp(powf(iAudioVolume, 2.5f), 0.0f, 0.3f);
+        #pragma unroll 10
+        for (int t = 0; t < 90; t++) {
+            const float2 d = c_blur.tap[t];
+            sum = sum + bg.stexture255(background_uv + mk2(d.x, d.y)*intensity);
+        }
+    }
+    // (first tap + 90 taps) / (quality*directions), unorm decode folded in
+    vec3 rgb = sum*((1.0f/255.0f)/(10.0f*8.0f));
+    rgb = rgb*(1.0f + 5.0f*iAudioSTD*powf(clamp(length(f.agluv) - 0.3f, 0.0f, 1.0f), 6.0f));
+
+    // rotate2d(-PI/2): cos = -4.371139e-08, sin = -1 in float32
+    const float c = -4.37113883e-08f, sn = -1.0f;
+    vec2 music_uv = mk2(c*uv.x + sn*uv.y, (-sn)*uv.x + c*uv.y);
+    music_uv = music_uv*(1.0f - 0.4f*powf(fabsf(iAudioVolume), 0.5f));
+    const float radius = 0.17f;
+    const float circle = fabsf(atan1n(music_uv));
+    vec4 s = texture<false>(P.tex[1], mk2(0.0f, circle));
+    vec2 freq = mk2(sqrtf(s.x/1000.0f), sqrtf(s.y/1000.0f));
+    freq = freq*(0.05f + 3.0f*smoothstep(0.0f, 2.0f, circle));
+    const float lm = length(music_uv);
+    if (lm < radius) {
+        rgb = rgb*0.5f;
+    } else {
+        const float bar = (music_uv.y < 0.0f) ? freq.x : freq.y;
+        const float r = radius + 0.5f*bar;
+        if (lm < r) rgb = mix(rgb, mk3(1.0f), smoothstep(0.0f, 1.0f, 0.5f + bar));
+        else        rgb = rgb*powf((lm - r)*0.5f, 0.05f);
+    }
+    rgb = mix(rgb, space, smoothstep(0.0f, 1.0f, length(uv)/20.0f));
+    vec2 vig = f.astuv*(1.0f - yx(f.astuv));
+    rgb = rgb*powf(vig.x*vig.y*20.0f, 0.1f + 0.15f*iAudioVolume);
+    vec4 fragColor = mk4(rgb, 1.0f);
+    vec4 w = texture<false>(P.tex[2], mk2(f.astuv.x, 0.0f));
+    if (1.0f - f.gluv.y < 0.2f*w.x) fragColor = fragColor*0.8f;
+    if (1.0f + f.gluv.y < 0.2f*w.y) fragColor = fragColor*0.8f;
+    return fragColor;
+}
+
 template <int SCENE, bool HW>
 SFB_DEV vec4 shade(const RenderParams& P, const Frag& f) {
     if constexpr (SCENE == SFB_SCENE_DEFAULT)    return scene_default<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_SHADERTOY)  return scene_shadertoy<HW>(P, f);
-    if constexpr (SCENE == SFB_SCENE_VISUALIZER) return scene_visualizer<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_VISUALIZER) {
+        if (!HW && P.fast) return scene_visualizer_fast(P, f);
+        return scene_visualizer<HW>(P, f);
+    }
     if constexpr (SCENE == SFB_SCENE_BARS)       return scene_bars<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_WAVEFORM)   return scene_waveform<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_MANDELBROT) return scene_mandelbrot<HW>(P, f);

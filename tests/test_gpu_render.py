@@ -133,6 +133,26 @@ def test_unfused_final_pass_general_filters(ctx, ssaa, subsample, scene_inputs):
         ctx.render_frame(2, N.Uniforms.defaults(W, H), [], W, H, 1, 2, 3, out)
 
 
+@pytest.mark.parametrize("volume", [0.0, 0.4, 1.6, 3.0])
+def test_fast_visualizer_path_equals_literal_transliteration(ctx, volume, scene_inputs):
+    """The production kernel (table-driven taps, quad cache, PRMT widening) against the literal
+    transliteration of visualizer.frag (SFB_RENDER_LITERAL): float32 re-association only"""
+    from shaderflow_b200 import _native as N
+    tex, extra, time = scene_inputs
+    extra = dict(extra, iAudioVolume=volume)
+    for (w, h) in ((W, H), (2*W, 2*H)):
+        u = uniforms_for("visualizer", extra, time)
+        _, fast, _ = gpu_screen(ctx, "visualizer", u, tex, w, h, N.FILTER_EXACT)
+        _, literal, _ = gpu_screen(ctx, "visualizer", u, tex, w, h, N.RENDER_LITERAL)
+        err = np.abs(fast[..., :3] - literal[..., :3])
+        assert err.max() < 5e-6, (volume, err.max())
+    # a background zoomed past the texture edge exercises the wrap branch of the quad fetch
+    u = uniforms_for("visualizer", extra, time, iCameraZoom=1.6)
+    _, fast, _ = gpu_screen(ctx, "visualizer", u, tex, W, H, N.FILTER_EXACT)
+    _, literal, _ = gpu_screen(ctx, "visualizer", u, tex, W, H, N.RENDER_LITERAL)
+    assert np.abs(fast[..., :3] - literal[..., :3]).max() < 5e-6
+
+
 def test_hardware_filter_mode_error_is_reported(ctx, scene_inputs):
     """SFB_FILTER_HARDWARE (cudaTextureObject, 9-bit weights) is opt-in; its deviation from the exact
     path stays within what 1.8 fixed-point weights allow"""

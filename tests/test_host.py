@@ -165,3 +165,12 @@ def test_camera_basis_and_scripted_rotation():
     cam.rotation.value = cam.rotation.target
     assert np.allclose(cam.forward, (1, 0, 0), atol=1e-12) and np.allclose(cam.right, (0, 0, -1), atol=1e-12)
     assert abs(cam.fov - 90.0) < 1e-9
+
+
+def test_synthetic_inputs_agree_with_the_oracle_copies():
+    from oracle import glsl_np as G
+    from shaderflow_b200 import synthetic
+    assert np.array_equal(synthetic.chirp(0.5), A.synth_chirp(0.5))
+    assert np.array_equal(synthetic.noise(0.2, seed=3), A.synth_noise(0.2, seed=3))
+    assert np.array_equal(synthetic.sine(0.1), A.synth_sine(0.1))
+    assert np.array_equal(synthetic.background(96, 54), G.synthetic_background(96, 54))
