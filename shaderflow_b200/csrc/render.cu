@@ -2,6 +2,9 @@
 // Reference call sites replaced: shader.py:367-405 (render / render_to_fbo), scene.py:185-194
 // (iFinal / iScreen programs), resources/shaders/fragment/final.glsl.
 #include "scenes.cuh"
+#include "visualizer_tiled.cuh"
+
+#include <cudaTypedefs.h>
 
 using namespace glsl;
 
@@ -201,6 +204,7 @@ static int build_blur_table() {
         }
     }
     if (n != 90) SFB_FAIL(SFB_ESTATE, "blur table has %d taps, expected 90", n);
+    table.tap[90] = make_float2(0.0f, 0.0f); table.tap[91] = make_float2(0.0f, 0.0f);
     SFB_CUDA(cudaMemcpyToSymbol(c_blur, &table, sizeof(table)));
     if (device < 64) done[device] = true;
     return SFB_OK;
@@ -254,6 +258,36 @@ template <int S, bool HW> struct LaunchFrame {
     }
 };
 
+// 2D tensor map over the background's linear mirror, one RGBA8 texel = one uint32 element, box 64x32
+static bool background_tensor_map(sfb_tex* t, CUtensorMap* out) {
+    if (t->external || t->dtype != SFB_DTYPE_U8 || t->padded != 4 || (t->w % 4) != 0 || t->w < VT_TMA_W || t->h < VT_TMA_H)
+        return false;
+    if (!t->tmap_tried) {
+        t->tmap_tried = true;
+        static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+                return false;
+            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        }
+        cuuint64_t dims[2] = {cuuint64_t(t->w), cuuint64_t(t->h)};
+        cuuint64_t strides[1] = {cuuint64_t(t->w)*4};
+        cuuint32_t box[2] = {VT_TMA_W, VT_TMA_H}, estr[2] = {1, 1};
+        CUresult rc = encode(reinterpret_cast<CUtensorMap*>(t->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, t->lin, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        t->tmap_ok = (rc == CUDA_SUCCESS);
+    }
+    if (t->tmap_ok) memcpy(out, t->tmap, sizeof(CUtensorMap));
+    return t->tmap_ok;
+}
+
+template <int S> static void launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
+    dim3 block(VT_TILE_X, VT_TILE_Y), grid((VP.R.W + VT_TILE_X - 1)/VT_TILE_X, (VP.R.H + VT_TILE_Y - 1)/VT_TILE_Y);
+    visualizer_tiled_kernel<S><<<grid, block, 0, st>>>(VP);
+}
+
 extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
                                  sfb_tex* const* samplers, int n_samplers, int flags,
                                  int target_w, int target_h, void* dst_rgba8_dev, float* dst_f32_dev) {
@@ -300,6 +334,21 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     P.Wr = width*ssaa; P.Hr = height*ssaa;
     P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
     P.dst = static_cast<unsigned char*>(dst_dev);
+    if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && ssaa <= 4) {
+        // production path of the headline scene: shared-memory window of the background per CTA
+        VisualizerParams VP;
+        memset(&VP.tmap, 0, sizeof(VP.tmap));
+        VP.R = P;
+        VP.use_tma = background_tensor_map(samplers[0], &VP.tmap) ? 1 : 0;
+        switch (ssaa) {
+            case 1: launch_visualizer_tiled<1>(VP, ctx->stream); break;
+            case 2: launch_visualizer_tiled<2>(VP, ctx->stream); break;
+            case 3: launch_visualizer_tiled<3>(VP, ctx->stream); break;
+            default: launch_visualizer_tiled<4>(VP, ctx->stream); break;
+        }
+        SFB_LAUNCH_CHECK(ctx);
+        return SFB_OK;
+    }
     dispatch<LaunchFrame>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;

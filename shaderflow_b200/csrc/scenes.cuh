@@ -288,7 +288,7 @@ SFB_DEV vec4 scene_raymarch(const RenderParams& P, const Frag& f) {
 //     registers and refetched only when (i0, j0) changes.
 // Differences to the literal path are float32 re-association only (~1e-7 relative).
 
-struct BlurTable { float2 tap[90]; };
+struct BlurTable { float2 tap[92]; };   // [0,90): dir*walk; [90] = (0,0), the undisplaced first tap
 __constant__ BlurTable c_blur;
 
 struct QuadSampler {

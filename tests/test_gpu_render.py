@@ -145,12 +145,12 @@ def test_fast_visualizer_path_equals_literal_transliteration(ctx, volume, scene_
         _, fast, _ = gpu_screen(ctx, "visualizer", u, tex, w, h, N.FILTER_EXACT)
         _, literal, _ = gpu_screen(ctx, "visualizer", u, tex, w, h, N.RENDER_LITERAL)
         err = np.abs(fast[..., :3] - literal[..., :3])
-        assert err.max() < 5e-6, (volume, err.max())
+        assert err.max() < 2e-5, (volume, err.max())
     # a background zoomed past the texture edge exercises the wrap branch of the quad fetch
     u = uniforms_for("visualizer", extra, time, iCameraZoom=1.6)
     _, fast, _ = gpu_screen(ctx, "visualizer", u, tex, W, H, N.FILTER_EXACT)
     _, literal, _ = gpu_screen(ctx, "visualizer", u, tex, W, H, N.RENDER_LITERAL)
-    assert np.abs(fast[..., :3] - literal[..., :3]).max() < 5e-6
+    assert np.abs(fast[..., :3] - literal[..., :3]).max() < 2e-5
 
 
 def test_hardware_filter_mode_error_is_reported(ctx, scene_inputs):
