@@ -5,6 +5,7 @@
 #include "visualizer_tiled.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 using namespace glsl;
 
@@ -259,16 +260,18 @@ template <int S, bool HW> struct LaunchFrame {
 };
 
 // 2D tensor map over the background's linear mirror, one RGBA8 texel = one uint32 element, box 64x32
-static bool background_tensor_map(sfb_tex* t, CUtensorMap* out) {
+static const CUtensorMap* background_tensor_map(sfb_tex* t) {
+    static const bool disabled = getenv("SFB_NO_TMA") != nullptr;      // debugging knob
+    if (disabled) return nullptr;
     if (t->external || t->dtype != SFB_DTYPE_U8 || t->padded != 4 || (t->w % 4) != 0 || t->w < VT_TMA_W || t->h < VT_TMA_H)
-        return false;
+        return nullptr;
     if (!t->tmap_tried) {
         t->tmap_tried = true;
         static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
         if (!encode) {
             void* fn = nullptr; cudaDriverEntryPointQueryResult q;
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-                return false;
+                return nullptr;
             encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
         }
         cuuint64_t dims[2] = {cuuint64_t(t->w), cuuint64_t(t->h)};
@@ -278,9 +281,12 @@ static bool background_tensor_map(sfb_tex* t, CUtensorMap* out) {
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         t->tmap_ok = (rc == CUDA_SUCCESS);
+        if (t->tmap_ok) {   // the kernel reads the descriptor from global memory
+            t->tmap_ok = cudaMalloc(&t->tmap_dev, sizeof(CUtensorMap)) == cudaSuccess
+                      && cudaMemcpy(t->tmap_dev, t->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
     }
-    if (t->tmap_ok) memcpy(out, t->tmap, sizeof(CUtensorMap));
-    return t->tmap_ok;
+    return t->tmap_ok ? static_cast<const CUtensorMap*>(t->tmap_dev) : nullptr;
 }
 
 template <int S> static void launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
@@ -337,9 +343,9 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && ssaa <= 4) {
         // production path of the headline scene: shared-memory window of the background per CTA
         VisualizerParams VP;
-        memset(&VP.tmap, 0, sizeof(VP.tmap));
         VP.R = P;
-        VP.use_tma = background_tensor_map(samplers[0], &VP.tmap) ? 1 : 0;
+        VP.tmap = background_tensor_map(samplers[0]);
+        VP.use_tma = VP.tmap ? 1 : 0;
         switch (ssaa) {
             case 1: launch_visualizer_tiled<1>(VP, ctx->stream); break;
             case 2: launch_visualizer_tiled<2>(VP, ctx->stream); break;

@@ -53,6 +53,7 @@ struct sfb_tex {
     const void* external = nullptr;
     bool tmap_tried = false, tmap_ok = false;
     alignas(64) unsigned char tmap[128] = {};   // CUtensorMap over `lin` (visualizer window loads)
+    void* tmap_dev = nullptr;                   // its device copy
     bool array_stale = false;          // rendered into through sfb_tex_storage: cudaArray copy is old
     int w = 0, h = 0, comps = 0, padded = 0, dtype = 0, filter = 0, rx = 1, ry = 1;
     size_t texel_bytes() const { return size_t(padded)*(dtype == SFB_DTYPE_U8 ? 1 : (dtype == SFB_DTYPE_F16 ? 2 : 4)); }

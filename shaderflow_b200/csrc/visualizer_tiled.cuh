@@ -9,7 +9,8 @@
 //      min/max gives the window (origin x0,y0; <= 64 x 32 texels);
 //   B. the window is staged ONCE into shared memory, already wrapped (REPEAT / CLAMP_TO_EDGE resolved
 //      per texel) and already widened from RGBA8 to float — by a TMA 2D tile load of the raw texels
-//      when the window lies inside the texture (cp.async.bulk.tensor, UTMALDG in SASS) followed by an
+//      when the window lies inside the texture (cp.async.bulk.tensor, UTMALDG in SASS; the box must start
+//      on a 16-byte boundary, so x0 is a multiple of 4 texels) followed by an
 //      in-place widen, or by plain loads when it crosses an edge;
 //   C. the 91 taps per fragment then cost: 2 FFMA for the position (tap table in the constant bank),
 //      a magic-constant floor (no F2I/FRND on the quarter-rate XU pipe), 4 LDS.128, 5 ops for the four
@@ -31,8 +32,8 @@ constexpr int VT_WIN_W = 64, VT_WIN_H = 32;            // background window capa
 constexpr int VT_TMA_W = 64, VT_TMA_H = 32;            // TMA box (texels)
 
 struct VisualizerParams {
-    CUtensorMap tmap;                                  // 2D uint32 view of the background's linear mirror (64-byte aligned)
     RenderParams R;
+    const CUtensorMap* tmap;                           // device copy of the 2D uint32 view of the background's linear mirror
     int use_tma;
 };
 
@@ -53,7 +54,7 @@ SFB_DEV void mbar_wait(unsigned long long* bar, unsigned int phase) {
     } while (!done);
 }
 SFB_DEV void tma_load_2d(void* dst, const void* tmap, unsigned long long* bar, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 
@@ -157,7 +158,8 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
         float ax = red[0][0], ay = red[1][0], bx = red[2][0], by = red[3][0];
         for (int r = 1; r < VT_TILE_Y; r++) { ax = fminf(ax, red[0][r]); ay = fminf(ay, red[1][r]); bx = fmaxf(bx, red[2][r]); by = fmaxf(by, red[3][r]); }
         const float reach = scale*1.0001f + 1.0f;             // |dir*walk| <= 1.0000001; +1 keeps local coords >= 1
-        const int x0 = int(floorf(ax - reach)) - 1, y0 = int(floorf(ay - reach)) - 1;
+        // TMA needs the box to start on a 16-byte boundary of the innermost dimension: x0 % 4 == 0
+        const int x0 = (int(floorf(ax - reach)) - 1) & ~3, y0 = int(floorf(ay - reach)) - 1;
         const int x1 = int(floorf(bx + reach)) + 2, y1 = int(floorf(by + reach)) + 2;   // inclusive last texel touched + 1
         const bool finite = (ax == ax) && (bx == bx) && (ay == ay) && (by == by) && fabsf(ax) < 1.0e9f && fabsf(bx) < 1.0e9f
                          && fabsf(ay) < 1.0e9f && fabsf(by) < 1.0e9f;
@@ -168,7 +170,7 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
             // ---- B1. TMA: the raw RGBA8 box lands in the FIRST 8 KB of the window buffer -------------
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bar, VT_TMA_W*VT_TMA_H*4);
-            tma_load_2d(window, &VP.tmap, &bar, x0, y0);
+            tma_load_2d(window, VP.tmap, &bar, x0, y0);
         }
     }
     __syncthreads();
