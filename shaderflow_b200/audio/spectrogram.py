@@ -87,7 +87,7 @@ def _kind(fn, default: int = 0) -> int:
     return getattr(getattr(fn, "__wrapped__", fn), "kind", default)
 
 
-@define(eq=False)
+@define(eq=False, slots=False)
 class BrokenSpectrogram:
     audio: BrokenAudio = Factory(BrokenAudio)
     fft_n: int = field(default=12, converter=int)

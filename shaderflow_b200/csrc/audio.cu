@@ -77,8 +77,22 @@ template <int R> __device__ __forceinline__ void dftR(cpx* v) {
 // Padded index into the data buffer: one extra slot every 16 keeps the radix-16 scatter conflict-free
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
+// Twiddle tables. For the pass with sub-transform size Ns and radix R a butterfly at k = j mod Ns needs
+// w^r, w = exp(-2*pi*i*k/(Ns*R)), r = 1..R-1. Only the power-of-two members w^1, w^2, w^4, w^8 are tabled —
+// laid out [m][k] so a warp reads consecutive entries (no bank conflicts) — and the rest are products of
+// at most three table values (<= 3-4 ulp). Pass 1 (Ns = 1) needs none.
+template <int LOG2N> struct TwiddleLayout {
+    static constexpr int N = 1 << LOG2N, FULL = LOG2N/4, REM = LOG2N%4;
+    // offset of pass p (p >= 1) in float2 entries; pass p has Ns = 16^p and log2(R) rows
+    static constexpr int rows(int p) { return (p < FULL) ? 4 : REM; }
+    static constexpr int ns(int p) { int v = 1; for (int i = 0; i < p; i++) v *= 16; return v; }
+    static constexpr int offset(int p) { int o = 0; for (int q = 1; q < p; q++) o += rows(q)*ns(q); return o; }
+    static constexpr int passes = FULL + (REM ? 1 : 0);
+    static constexpr int total = offset(passes);
+};
+
 // One in-place Stockham pass of radix R over N points held in `buf`; each thread owns 16/R butterflies.
-// Ns = product of the radices of the previous passes.
+// Ns = product of the radices of the previous passes; `tw` = this pass's table ([log2 R][Ns]).
 template <int LOG2N, int R>
 __device__ __forceinline__ void stockham_pass(cpx* buf, const float2* tw, int Ns, int tid) {
     constexpr int N = 1 << LOG2N, T = N/16, M = 16/R;
@@ -91,12 +105,13 @@ __device__ __forceinline__ void stockham_pass(cpx* buf, const float2* tw, int Ns
             for (int r = 0; r < R; r++) v[m][r] = buf[pad(j + r*(N/R))];
             if (Ns > 1) {
                 const int k = j & (Ns - 1);
-                const int step = k*(N/(Ns*R));             // twiddle index of r=1
+                cpx w[R];
                 #pragma unroll
-                for (int r = 1; r < R; r++) {
-                    const float2 w = tw[(r*step) & (N - 1)];
-                    v[m][r] = cmul(v[m][r], cpx{w.x, w.y});
-                }
+                for (int b = 0, r = 1; r < R; r <<= 1, b++) { const float2 t = tw[b*Ns + k]; w[r] = cpx{t.x, t.y}; }
+                #pragma unroll
+                for (int r = 3; r < R; r++) if (r & (r - 1)) w[r] = cmul(w[r & (r - 1)], w[r & -r]);   // clear lowest bit x lowest bit
+                #pragma unroll
+                for (int r = 1; r < R; r++) v[m][r] = cmul(v[m][r], w[r]);
             }
             dftR<R>(v[m]);
         }
@@ -117,13 +132,14 @@ __device__ __forceinline__ void stockham_pass(cpx* buf, const float2* tw, int Ns
 
 template <int LOG2N>
 __device__ __forceinline__ void fft_inplace(cpx* buf, const float2* tw, int tid) {
+    using L = TwiddleLayout<LOG2N>;
     constexpr int FULL = LOG2N/4, REM = LOG2N%4;
     int Ns = 1;
     #pragma unroll
-    for (int p = 0; p < FULL; p++) { stockham_pass<LOG2N, 16>(buf, tw, Ns, tid); Ns *= 16; }
-    if constexpr (REM == 1) stockham_pass<LOG2N, 2>(buf, tw, Ns, tid);
-    if constexpr (REM == 2) stockham_pass<LOG2N, 4>(buf, tw, Ns, tid);
-    if constexpr (REM == 3) stockham_pass<LOG2N, 8>(buf, tw, Ns, tid);
+    for (int p = 0; p < FULL; p++) { stockham_pass<LOG2N, 16>(buf, tw + L::offset(p), Ns, tid); Ns *= 16; }
+    if constexpr (REM == 1) stockham_pass<LOG2N, 2>(buf, tw + L::offset(FULL), Ns, tid);
+    if constexpr (REM == 2) stockham_pass<LOG2N, 4>(buf, tw + L::offset(FULL), Ns, tid);
+    if constexpr (REM == 3) stockham_pass<LOG2N, 8>(buf, tw + L::offset(FULL), Ns, tid);
 }
 
 struct StftParams {
@@ -145,16 +161,16 @@ __device__ __forceinline__ float apply_volume(int kind, float x) {
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__((1 << LOG2N)/16 < 32 ? 32 : (1 << LOG2N)/16)
+__global__ void __launch_bounds__((1 << LOG2N)/16 < 32 ? 32 : (1 << LOG2N)/16, ((1 << LOG2N) <= 4096) ? 3 : 1)
 stft_mel_kernel(const __grid_constant__ StftParams P) {
-    constexpr int N = 1 << LOG2N, BINS = N/2 + 1;
+    constexpr int N = 1 << LOG2N, BINS = N/2 + 1, TW = TwiddleLayout<LOG2N>::total;
     extern __shared__ __align__(16) unsigned char smem[];
     cpx*    buf = reinterpret_cast<cpx*>(smem);                               // pad(N) complex
-    float2* tw  = reinterpret_cast<float2*>(smem + sizeof(cpx)*(N + N/16));   // N twiddles
+    float2* tw  = reinterpret_cast<float2*>(smem + sizeof(cpx)*(N + N/16));   // per-pass twiddle tables
     float*  mag = reinterpret_cast<float*>(smem);                             // [2][BINS], aliases buf after the FFT
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
-    for (int i = tid; i < N; i += nthreads) tw[i] = P.twiddle[i];
+    for (int i = tid; i < TW; i += nthreads) tw[i] = P.twiddle[i];
 
     for (int frame = blockIdx.x; frame < P.n_frames; frame += gridDim.x) {
         __syncthreads();
@@ -165,27 +181,31 @@ stft_mel_kernel(const __grid_constant__ StftParams P) {
                 for (int n = tid; n < N; n += nthreads) buf[pad(n)].y = 0.0f;
                 continue;
             }
-            const float* x = P.pcm + (long long)c*P.n_samples;
-            // first index ≤ lo whose address is 16-byte aligned
-            const long long mis = (long long)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);
-            long long base = lo - (((lo + mis) % 4 + 4) % 4);
-            for (long long q = base + 4LL*tid; q < lo + N; q += 4LL*nthreads) {
-                float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (q >= 0 && q + 3 < P.n_samples) {
-                    s = __ldg(reinterpret_cast<const float4*>(x + q));
+            // x0 = first sample of the window (may point before the clip: guarded below); all indexing
+            // below is 32-bit relative to it
+            const float* x0 = P.pcm + (long long)c*P.n_samples + lo;
+            const int before = (lo < 0) ? int(-lo > N ? N : -lo) : 0;              // window samples before the clip start
+            const long long room = P.n_samples - lo;
+            const int avail = room > N ? N : (room < 0 ? 0 : int(room));          // window samples inside the clip
+            // first offset <= 0 whose address is 16-byte aligned
+            const int mis = int((reinterpret_cast<uintptr_t>(x0) >> 2) & 3);
+            for (int q = 4*tid - mis; q < N; q += 4*nthreads) {
+                float4 s;
+                if (q >= before && q + 3 < avail) {
+                    s = __ldg(reinterpret_cast<const float4*>(x0 + q));
                 } else {
-                    if (q + 0 >= 0 && q + 0 < P.n_samples) s.x = __ldg(x + q + 0);
-                    if (q + 1 >= 0 && q + 1 < P.n_samples) s.y = __ldg(x + q + 1);
-                    if (q + 2 >= 0 && q + 2 < P.n_samples) s.z = __ldg(x + q + 2);
-                    if (q + 3 >= 0 && q + 3 < P.n_samples) s.w = __ldg(x + q + 3);
+                    s.x = (q + 0 >= before && q + 0 < avail) ? __ldg(x0 + q + 0) : 0.0f;
+                    s.y = (q + 1 >= before && q + 1 < avail) ? __ldg(x0 + q + 1) : 0.0f;
+                    s.z = (q + 2 >= before && q + 2 < avail) ? __ldg(x0 + q + 2) : 0.0f;
+                    s.w = (q + 3 >= before && q + 3 < avail) ? __ldg(x0 + q + 3) : 0.0f;
                 }
                 const float e[4] = {s.x, s.y, s.z, s.w};
                 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    const long long n = q + t - lo;
+                    const int n = q + t;
                     if (n >= 0 && n < N) {
                         const float w = e[t]*__ldg(P.window + n);
-                        if (c == 0) buf[pad(int(n))].x = w; else buf[pad(int(n))].y = w;
+                        if (c == 0) buf[pad(n)].x = w; else buf[pad(n)].y = w;
                     }
                 }
             }
@@ -252,13 +272,23 @@ stft_mel_kernel(const __grid_constant__ StftParams P) {
 static int stft_tables(sfb_ctx* ctx, int fft_n, int window_kind) {
     const int N = 1 << fft_n;
     if (!ctx->twiddle[fft_n]) {
-        std::vector<float2> tw(N);
-        for (int m = 0; m < N; m++) {
-            const double a = -2.0*M_PI*double(m)/double(N);
-            tw[m] = make_float2(float(cos(a)), float(sin(a)));
+        // per-pass tables [log2 R][Ns] of exp(-2*pi*i * m*k/(Ns*R)), m = 1, 2, 4, 8 (see TwiddleLayout)
+        std::vector<float2> tw;
+        const int full = fft_n/4, rem = fft_n%4;
+        int Ns = 1;
+        for (int p = 0; p < full + (rem ? 1 : 0); p++) {
+            const int R = (p < full) ? 16 : (1 << rem);
+            if (p >= 1)
+                for (int m = 1; m < R; m <<= 1)
+                    for (int k = 0; k < Ns; k++) {
+                        const double a = -2.0*M_PI*double(m)*double(k)/(double(Ns)*double(R));
+                        tw.push_back(make_float2(float(cos(a)), float(sin(a))));
+                    }
+            Ns *= R;
         }
-        SFB_CUDA(cudaMalloc(&ctx->twiddle[fft_n], sizeof(float2)*N));
-        SFB_CUDA(cudaMemcpy(ctx->twiddle[fft_n], tw.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
+        if (tw.empty()) tw.push_back(make_float2(1.0f, 0.0f));
+        SFB_CUDA(cudaMalloc(&ctx->twiddle[fft_n], sizeof(float2)*tw.size()));
+        SFB_CUDA(cudaMemcpy(ctx->twiddle[fft_n], tw.data(), sizeof(float2)*tw.size(), cudaMemcpyHostToDevice));
     }
     if (!ctx->window[window_kind][fft_n]) {
         std::vector<float> w(N);
@@ -280,7 +310,7 @@ template <int LOG2N>
 static int stft_launch(sfb_ctx* ctx, const StftParams& P) {
     constexpr int N = 1 << LOG2N;
     const int threads = (N/16 < 32) ? 32 : N/16;
-    const size_t smem = sizeof(cpx)*(N + N/16) + sizeof(float2)*N;
+    const size_t smem = sizeof(cpx)*(N + N/16) + sizeof(float2)*(TwiddleLayout<LOG2N>::total > 0 ? TwiddleLayout<LOG2N>::total : 1);
     static bool configured[16] = {};
     auto kernel = stft_mel_kernel<LOG2N>;
     if (!configured[LOG2N]) {

@@ -174,3 +174,17 @@ def test_synthetic_inputs_agree_with_the_oracle_copies():
     assert np.array_equal(synthetic.noise(0.2, seed=3), A.synth_noise(0.2, seed=3))
     assert np.array_equal(synthetic.sine(0.1), A.synth_sine(0.1))
     assert np.array_equal(synthetic.background(96, 54), G.synthetic_background(96, 54))
+
+
+def test_standalone_spectrogram_matrix_matches_reference_golden(golden_dir):
+    """BrokenSpectrogram outside a scene: the CSR filterbank equals the reference's (piano and default banks)"""
+    from shaderflow_b200.audio import BrokenAudio, BrokenSpectrogram
+    for name, notes in (("audio_c1_sine", (15, 129)), ("audio_chirp_1000", None)):
+        gold = np.load(golden_dir/f"{name}.npz")
+        spec = BrokenSpectrogram(audio=BrokenAudio())
+        if notes:
+            spec.from_notes(*notes, piano=True)
+        m = spec.spectrogram_matrix()
+        assert np.array_equal(m.indptr, gold["bank_indptr"]) and np.array_equal(m.indices, gold["bank_indices"])
+        assert np.array_equal(m.data, gold["bank_data"]) and np.array_equal(spec.spectrogram_frequencies, gold["bank_frequencies"])
+        assert spec.spectrogram_matrix() is m      # cached per configuration
