@@ -289,9 +289,16 @@ static const CUtensorMap* background_tensor_map(sfb_tex* t) {
     return t->tmap_ok ? static_cast<const CUtensorMap*>(t->tmap_dev) : nullptr;
 }
 
-template <int S> static void launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
+template <int S> static cudaError_t launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(visualizer_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VT_SMEM));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     dim3 block(VT_TILE_X, VT_TILE_Y), grid((VP.R.W + VT_TILE_X - 1)/VT_TILE_X, (VP.R.H + VT_TILE_Y - 1)/VT_TILE_Y);
-    visualizer_tiled_kernel<S><<<grid, block, 0, st>>>(VP);
+    visualizer_tiled_kernel<S><<<grid, block, VT_SMEM, st>>>(VP);
+    return cudaSuccess;
 }
 
 extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
@@ -346,12 +353,14 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
         VP.R = P;
         VP.tmap = background_tensor_map(samplers[0]);
         VP.use_tma = VP.tmap ? 1 : 0;
+        cudaError_t e;
         switch (ssaa) {
-            case 1: launch_visualizer_tiled<1>(VP, ctx->stream); break;
-            case 2: launch_visualizer_tiled<2>(VP, ctx->stream); break;
-            case 3: launch_visualizer_tiled<3>(VP, ctx->stream); break;
-            default: launch_visualizer_tiled<4>(VP, ctx->stream); break;
+            case 1: e = launch_visualizer_tiled<1>(VP, ctx->stream); break;
+            case 2: e = launch_visualizer_tiled<2>(VP, ctx->stream); break;
+            case 3: e = launch_visualizer_tiled<3>(VP, ctx->stream); break;
+            default: e = launch_visualizer_tiled<4>(VP, ctx->stream); break;
         }
+        SFB_CUDA(e);
         SFB_LAUNCH_CHECK(ctx);
         return SFB_OK;
     }

@@ -12,9 +12,15 @@
 //      when the window lies inside the texture (cp.async.bulk.tensor, UTMALDG in SASS; the box must start
 //      on a 16-byte boundary, so x0 is a multiple of 4 texels) followed by an
 //      in-place widen, or by plain loads when it crosses an edge;
-//   C. the 91 taps per fragment then cost: 2 FFMA for the position (tap table in the constant bank),
-//      a magic-constant floor (no F2I/FRND on the quarter-rate XU pipe), 4 LDS.128, 5 ops for the four
-//      weights and 12 FFMA — no integer modulo, no byte unpacking, no global loads;
+//   C. the taps per fragment then cost: 2 FFMA for the position (tap table in the constant bank), a
+//      magic-constant floor (no F2I/FRND on the quarter-rate XU pipe), 2 LDS.128 + 2 LDS.64, 5 ops for
+//      the four weights and 12 FFMA — no integer modulo, no byte unpacking, no global loads.
+//      The kernel is bound by shared-memory wavefronts (ncu: 87 % of peak with one float4 per texel), so
+//      the window is stored as horizontal PAIR records — rg[y][x] = (r,g) of texels x and x+1 (float4),
+//      bb[y][x] = b of texels x and x+1 (float2) — which serves a bilinear footprint in 12 wavefronts
+//      instead of 16. The 9th direction of the float loop (angle 8*(TAU/8) = 6.2831850 < TAU) coincides
+//      with the first to 1e-6 texel, below the float32 resolution of the tap position itself, so ray 0 is
+//      evaluated once and weighted twice: 81 footprints stand for the 91 taps;
 //   D. the rest of main() per fragment, the RGBA8 store rule per sub-sample, the integer box sum and
 //      the rgb24 store (staged through shared memory so rows leave as 32-bit words).
 // Arithmetic differs from the literal transliteration (scenes.cuh: scene_visualizer) only by float32
@@ -56,13 +62,6 @@ SFB_DEV void mbar_wait(unsigned long long* bar, unsigned int phase) {
 SFB_DEV void tma_load_2d(void* dst, const void* tmap, unsigned long long* bar, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-
-SFB_DEV float4 widen_rgba(unsigned int word) {
-    // byte k into the mantissa of 2^23 (PRMT), minus 2^23: exact, no I2F
-    return make_float4(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.0f,
-                       __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.0f,
-                       __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.0f, 0.0f);
 }
 
 // Per-fragment front end of main(): camera + background_uv → centre tap position in texel space
@@ -114,14 +113,25 @@ SFB_DEV vec4 vis_back(const RenderParams& P, const VisFrag& v, vec3 rgb) {
     return fragColor;
 }
 
+constexpr int VT_WIN = VT_WIN_W*VT_WIN_H;
+constexpr size_t VT_SMEM = sizeof(float4)*VT_WIN + sizeof(float2)*VT_WIN;     // rg pairs + b pairs = 48 KB (dynamic)
+
+SFB_DEV vec3 widen3(unsigned int word) {
+    return mk3(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)) - 8388608.0f,
+               __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)) - 8388608.0f,
+               __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)) - 8388608.0f);
+}
+
 template <int S>
-__global__ void __launch_bounds__(VT_TILE_X*VT_TILE_Y)
+__global__ void __launch_bounds__(VT_TILE_X*VT_TILE_Y, 4)
 visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
     const RenderParams& P = VP.R;
-    __shared__ __align__(128) float4 window[VT_WIN_H*VT_WIN_W];            // 32 KB
+    extern __shared__ __align__(128) unsigned char vt_smem[];
+    float4* rg = reinterpret_cast<float4*>(vt_smem);                        // [VT_WIN_H][VT_WIN_W] (r,g) of texels x, x+1
+    float2* bb = reinterpret_cast<float2*>(vt_smem + sizeof(float4)*VT_WIN);// [VT_WIN_H][VT_WIN_W] b of texels x, x+1
     __shared__ unsigned int stage[VT_TILE_Y][VT_TILE_X];
     __shared__ float red[4][VT_TILE_Y];
-    __shared__ int win[4];                                                  // x0, y0, fits
+    __shared__ int win[4];                                                  // x0, y0, fits, tma
     __shared__ __align__(8) unsigned long long bar;
 
     const int tid = threadIdx.y*VT_TILE_X + threadIdx.x;
@@ -160,17 +170,18 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
         const float reach = scale*1.0001f + 1.0f;             // |dir*walk| <= 1.0000001; +1 keeps local coords >= 1
         // TMA needs the box to start on a 16-byte boundary of the innermost dimension: x0 % 4 == 0
         const int x0 = (int(floorf(ax - reach)) - 1) & ~3, y0 = int(floorf(ay - reach)) - 1;
-        const int x1 = int(floorf(bx + reach)) + 2, y1 = int(floorf(by + reach)) + 2;   // inclusive last texel touched + 1
+        const int x1 = int(floorf(bx + reach)) + 2, y1 = int(floorf(by + reach)) + 2;   // last texel touched + 1
         const bool finite = (ax == ax) && (bx == bx) && (ay == ay) && (by == by) && fabsf(ax) < 1.0e9f && fabsf(bx) < 1.0e9f
                          && fabsf(ay) < 1.0e9f && fabsf(by) < 1.0e9f;
         win[0] = x0; win[1] = y0;
-        win[2] = (finite && (x1 - x0) <= VT_WIN_W && (y1 - y0) <= VT_WIN_H) ? 1 : 0;
+        // pair records need texel x+1 too: the last column of the window only ever serves as a neighbour
+        win[2] = (finite && (x1 - x0) <= VT_WIN_W - 1 && (y1 - y0) <= VT_WIN_H) ? 1 : 0;
         win[3] = (win[2] && VP.use_tma && x0 >= 0 && y0 >= 0 && x0 + VT_TMA_W <= bg.w && y0 + VT_TMA_H <= bg.h) ? 1 : 0;
         if (win[3]) {
             // ---- B1. TMA: the raw RGBA8 box lands in the FIRST 8 KB of the window buffer -------------
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bar, VT_TMA_W*VT_TMA_H*4);
-            tma_load_2d(window, VP.tmap, &bar, x0, y0);
+            tma_load_2d(vt_smem, VP.tmap, &bar, x0, y0);
         }
     }
     __syncthreads();
@@ -178,24 +189,36 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
     const bool fits = win[2] != 0;
 
     if (fits) {
+        constexpr int PER = VT_WIN/(VT_TILE_X*VT_TILE_Y);                  // window texels per thread (8)
+        unsigned int w0[PER], w1[PER];                                      // texel t and its right neighbour
         if (win[3]) {
             mbar_wait(&bar, 0);
-            // widen in place, back to front so no float4 overwrites a byte texel that is still needed:
-            // texel t lives at bytes [4t, 4t+4) and expands to bytes [16t, 16t+16)
-            const unsigned int* raw = reinterpret_cast<const unsigned int*>(window);
-            unsigned int words[(VT_WIN_W*VT_WIN_H)/(VT_TILE_X*VT_TILE_Y)];
+            const unsigned int* raw = reinterpret_cast<const unsigned int*>(vt_smem);
             #pragma unroll
-            for (int k = 0; k < (VT_WIN_W*VT_WIN_H)/(VT_TILE_X*VT_TILE_Y); k++) words[k] = raw[tid + k*VT_TILE_X*VT_TILE_Y];
-            __syncthreads();
-            #pragma unroll
-            for (int k = 0; k < (VT_WIN_W*VT_WIN_H)/(VT_TILE_X*VT_TILE_Y); k++) window[tid + k*VT_TILE_X*VT_TILE_Y] = widen_rgba(words[k]);
+            for (int k = 0; k < PER; k++) {
+                const int t = tid + k*VT_TILE_X*VT_TILE_Y;
+                w0[k] = raw[t];
+                w1[k] = raw[((t % VT_WIN_W) == VT_WIN_W - 1) ? t : t + 1];
+            }
+            __syncthreads();                                                 // raw box fully read before it is overwritten
         } else {
             // ---- B2. edge windows: per-texel wrap, plain loads -----------------------------------
             const unsigned int* texels = reinterpret_cast<const unsigned int*>(bg.lin);
-            for (int t = tid; t < VT_WIN_W*VT_WIN_H; t += VT_TILE_X*VT_TILE_Y) {
-                const int gx = wrap_index(x0 + (t % VT_WIN_W), bg.w, bg.rx), gy = wrap_index(y0 + (t / VT_WIN_W), bg.h, bg.ry);
-                window[t] = widen_rgba(__ldg(texels + size_t(gy)*size_t(bg.w) + size_t(gx)));
+            #pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int t = tid + k*VT_TILE_X*VT_TILE_Y;
+                const int gy = wrap_index(y0 + (t / VT_WIN_W), bg.h, bg.ry);
+                const unsigned int* row = texels + size_t(gy)*size_t(bg.w);
+                w0[k] = __ldg(row + wrap_index(x0 + (t % VT_WIN_W), bg.w, bg.rx));
+                w1[k] = __ldg(row + wrap_index(x0 + (t % VT_WIN_W) + 1, bg.w, bg.rx));
             }
+        }
+        #pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int t = tid + k*VT_TILE_X*VT_TILE_Y;
+            const vec3 a = widen3(w0[k]), b = widen3(w1[k]);
+            rg[t] = make_float4(a.x, a.y, b.x, b.y);
+            bb[t] = make_float2(a.z, b.z);
         }
     }
     __syncthreads();
@@ -206,7 +229,7 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
         #pragma unroll
         for (int s = 0; s < S*S; s++) {
             vec4 c;
-            // the per-fragment state is cheap next to 91 taps: recompute it instead of keeping it live
+            // the per-fragment state is cheap next to the taps: recompute it instead of keeping it live
             const VisFrag v = vis_front(P, x*S + (s % S), y*S + (s / S), fw, fh, hw, wobble, zf);
             if (v.oob) {
                 c = mk4(mk3(1.0f, 11.0f, 26.0f)/255.0f, 0.0f);
@@ -215,26 +238,38 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
             } else {
                 // tile-local centre, >= 1 by construction of x0/y0
                 const float cx = tap[s].x - float(x0), cy = tap[s].y - float(y0);
+                const char* rg_base = reinterpret_cast<const char*>(rg);
+                const char* bb_base = reinterpret_cast<const char*>(bb);
                 float ar = 0.0f, ag = 0.0f, ab = 0.0f;
-                const char* base = reinterpret_cast<const char*>(window);
-                #pragma unroll 7
-                for (int t = 0; t < 91; t++) {
-                    // t == 90 is the undisplaced first tap (visualizer.frag:18): table entry 90 is (0, 0)
-                    const float2 d = c_blur.tap[t];
-                    const float px = fmaf(d.x, scale, cx), py = fmaf(d.y, scale, cy);
+                auto footprint = [&](float dx, float dy) {
+                    const float px = fmaf(dx, scale, cx), py = fmaf(dy, scale, cy);
                     // floor for 0.5 <= p < 2^22: p + (2^23 - 0.5) rounds to the integer floor(p) + 2^23
                     // (ties land on either neighbour; bilinear interpolation is continuous there)
                     const float tx = px + 8388607.5f, ty = py + 8388607.5f;
                     const float a = px - (tx - 8388608.0f), b = py - (ty - 8388608.0f);
-                    const int off = (__float_as_int(ty) - 0x4B000000)*VT_WIN_W + (__float_as_int(tx) - 0x4B000000);
-                    const float4* q = reinterpret_cast<const float4*>(base + (size_t(off) << 4));
-                    const float4 t00 = q[0], t10 = q[1], t01 = q[VT_WIN_W], t11 = q[VT_WIN_W + 1];
+                    // 8*(iy*64 + ix), modulo 2^32: the 2^23 offsets of the magic constant fold into one constant
+                    const unsigned int off8 = ((unsigned int)__float_as_int(ty) << 9) + ((unsigned int)__float_as_int(tx) << 3)
+                                            - ((0x4B000000u << 9) + (0x4B000000u << 3));
+                    const float4 r0 = *reinterpret_cast<const float4*>(rg_base + 2u*off8);
+                    const float4 r1 = *reinterpret_cast<const float4*>(rg_base + 2u*off8 + VT_WIN_W*16);
+                    const float2 b0 = *reinterpret_cast<const float2*>(bb_base + off8);
+                    const float2 b1 = *reinterpret_cast<const float2*>(bb_base + off8 + VT_WIN_W*8);
                     const float w11 = a*b, w10 = a - w11, w01 = b - w11, w00 = (1.0f - a) - w01;
-                    ar = fmaf(w00, t00.x, ar); ag = fmaf(w00, t00.y, ag); ab = fmaf(w00, t00.z, ab);
-                    ar = fmaf(w10, t10.x, ar); ag = fmaf(w10, t10.y, ag); ab = fmaf(w10, t10.z, ab);
-                    ar = fmaf(w01, t01.x, ar); ag = fmaf(w01, t01.y, ag); ab = fmaf(w01, t01.z, ab);
-                    ar = fmaf(w11, t11.x, ar); ag = fmaf(w11, t11.y, ag); ab = fmaf(w11, t11.z, ab);
+                    ar = fmaf(w00, r0.x, ar); ag = fmaf(w00, r0.y, ag); ab = fmaf(w00, b0.x, ab);
+                    ar = fmaf(w10, r0.z, ar); ag = fmaf(w10, r0.w, ag); ab = fmaf(w10, b0.y, ab);
+                    ar = fmaf(w01, r1.x, ar); ag = fmaf(w01, r1.y, ag); ab = fmaf(w01, b1.x, ab);
+                    ar = fmaf(w11, r1.z, ar); ag = fmaf(w11, r1.w, ag); ab = fmaf(w11, b1.y, ab);
+                };
+                // ray 0 (angle 0) stands for itself and for the 9th float-loop direction: weight 2
+                #pragma unroll
+                for (int t = 0; t < 10; t++) footprint(c_blur.tap[t].x, c_blur.tap[t].y);
+                ar += ar; ag += ag; ab += ab;
+                #pragma unroll 1
+                for (int ray = 1; ray < 8; ray++) {
+                    #pragma unroll
+                    for (int t = 0; t < 10; t++) footprint(c_blur.tap[ray*10 + t].x, c_blur.tap[ray*10 + t].y);
                 }
+                footprint(0.0f, 0.0f);                                  // the undisplaced first tap (visualizer.frag:18)
                 c = vis_back(P, v, mk3(ar, ag, ab)*((1.0f/255.0f)/(10.0f*8.0f)));
             }
             r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
