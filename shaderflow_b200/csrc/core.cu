@@ -58,6 +58,7 @@ extern "C" int sfb_ctx_destroy(sfb_ctx* ctx) {
     for (auto& t : ctx->twiddle) if (t) cudaFree(t);
     for (auto& k : ctx->window) for (auto& w : k) if (w) cudaFree(w);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& b : ctx->ring_pool) { cudaFreeHost(b.host); cudaFree(b.dev); }
     delete ctx;
     return SFB_OK;
 }

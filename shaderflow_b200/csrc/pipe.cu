@@ -68,8 +68,16 @@ extern "C" int sfb_pipe_open(sfb_ctx* ctx, int fd, int n_buffers, size_t frame_b
     cudaError_t e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->rendered, cudaEventDisableTiming);
     for (auto& s : p->slots) {
-        if (e == cudaSuccess) e = cudaHostAlloc(&s.host, frame_bytes, cudaHostAllocDefault);
-        if (e == cudaSuccess) e = cudaMalloc(&s.dev, frame_bytes);
+        // reuse a pooled (pinned host, device) pair of the right size when the context has one
+        for (size_t i = 0; i < ctx->ring_pool.size() && !s.host; i++)
+            if (ctx->ring_pool[i].bytes == frame_bytes) {
+                s.host = ctx->ring_pool[i].host; s.dev = ctx->ring_pool[i].dev;
+                ctx->ring_pool.erase(ctx->ring_pool.begin() + i);
+            }
+        if (!s.host) {
+            if (e == cudaSuccess) e = cudaHostAlloc(&s.host, frame_bytes, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaMalloc(&s.dev, frame_bytes);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
@@ -142,7 +150,11 @@ extern "C" int sfb_pipe_close(sfb_pipe* p) {
     p->writer.join();
     const int err = p->io_errno;
     cudaStreamSynchronize(p->copy_stream);
-    for (auto& s : p->slots) { cudaFreeHost(s.host); cudaFree(s.dev); cudaEventDestroy(s.copied); }
+    for (auto& s : p->slots) {
+        cudaEventDestroy(s.copied);
+        if (p->ctx->ring_pool.size() < 16) p->ctx->ring_pool.push_back({s.host, s.dev, p->frame_bytes});
+        else { cudaFreeHost(s.host); cudaFree(s.dev); }
+    }
     cudaEventDestroy(p->rendered);
     cudaStreamDestroy(p->copy_stream);
     delete p;

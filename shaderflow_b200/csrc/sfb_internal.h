@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include <string.h>
 
 #include "../../include/sfb200.h"
@@ -29,6 +30,10 @@ struct sfb_ctx {
     // Scratch for sfb_audio_track
     void*  scratch = nullptr;
     size_t scratch_bytes = 0;
+    // Sink ring buffers kept across sfb_pipe_open/close: pinned host + device frame pairs (cudaHostAlloc
+    // of a 4K frame ring costs tens of ms, which a short export would pay every time)
+    struct RingBuffer { void* host; void* dev; size_t bytes; };
+    std::vector<RingBuffer> ring_pool;
 };
 
 int sfb_ctx_scratch(sfb_ctx* ctx, size_t bytes, void** out);
