@@ -56,13 +56,42 @@ def parse_args():
 # Clock sampling during the timed region (B200_PROFILING.md)
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 200 ms during the timed region, through NVML in a thread
+    (nvidia_ml_py); an `nvidia-smi -lms` child is the fallback. NVML in-process is the lighter of the two:
+    the nvidia-smi poller was measured to stall driver calls of the sink for hundreds of ms."""
+    REASONS = dict(hw_slowdown=0x8, hw_thermal_slowdown=0x40, sw_thermal_slowdown=0x20, sw_power_cap=0x4)
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.proc, self.path = device, None, None
+        self.device, self.proc, self.path, self.thread = device, None, None, None
+        self.sm, self.mx, self.reasons, self.stop_flag = [], [], set(), threading.Event()
+
+    def _nvml_loop(self, handle, nv):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[self.device]) if os.environ.get("CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else self.device
+            handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(handle, nv), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.path = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
@@ -73,25 +102,26 @@ class ClockSampler:
 
     def stop(self) -> dict:
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try: self.proc.wait(timeout=5)
-        except Exception: self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in Path(self.path).read_text().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, flag in zip(names, parts[5:9]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
+        sm, mx, reasons = self.sm, self.mx, self.reasons
+        if self.thread is not None:
+            self.stop_flag.set(); self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
+            try: self.proc.wait(timeout=5)
+            except Exception: self.proc.kill()
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            for line in Path(self.path).read_text().splitlines():
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, flag in zip(names, parts[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
         if sm:
             loaded = sorted(sm)[len(sm)//4:] if len(sm) > 4 else sm       # drop the idle tail
             out.update(sm_mhz=float(np.median(loaded)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
@@ -198,9 +228,13 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
     clocks = sampler.stop() if rank == 0 else {}
 
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         timed(step_e2e)
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
     e2e_ms = [timed(step_e2e) for _ in range(args.steps)]
+    clocks_e2e = sampler2.stop() if rank == 0 else {}
 
     if rank != 0:
         return
@@ -226,7 +260,7 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
                     gfragments_per_s=W*S*H*S/(kernel_avg_ms/1e3)/1e9)
 
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                ms_per_step=ms_per_step, ms_each_step=[round(float(m), 2) for m in value_ms], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=WORKLOAD, frames_per_step_per_gpu=F, global_frames_per_step=total_frames,
                             parallelism=f"frame-shard x{world} + gather to rank 0" if world > 1 else "single GPU",
                             filter="hardware" if args.hardware_filter else "exact",
@@ -234,7 +268,9 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
                                "across frames by design" % (F*W*H*3/1e9)),
                 clocks=dict(sm_mhz=clocks.get("sm_mhz"), sm_max_mhz=clocks.get("sm_max_mhz"), reasons=clocks.get("reasons", [])),
                 e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(clip.nbytes),
-                         d2h_bytes_per_step=int(total_frames*W*H*3), ms_per_step=float(np.mean(e2e_ms))),
+                         d2h_bytes_per_step=int(total_frames*W*H*3), ms_per_step=float(np.mean(e2e_ms)),
+                         ms_each_step=[round(float(m), 2) for m in e2e_ms], sm_mhz=clocks_e2e.get("sm_mhz"),
+                         reasons=clocks_e2e.get("reasons", [])),
                 gpu_launches=int(launches), roofline=roofline)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args)

@@ -230,6 +230,9 @@ int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
 int sfb_pipe_open(sfb_ctx* ctx, int fd, int n_buffers, size_t frame_bytes, sfb_pipe** out);
 int sfb_pipe_acquire(sfb_pipe* pipe, void** frame_dev);
 int sfb_pipe_submit(sfb_pipe* pipe, const void* frame_dev);
+/* Re-targets an idle ring (everything submitted has been written) at another file descriptor, so one ring —
+ * its pinned buffers, copy stream and writer thread — serves consecutive exports. */
+int sfb_pipe_set_fd(sfb_pipe* pipe, int fd);
 int sfb_pipe_sync(sfb_pipe* pipe);                       /* blocks until every submitted frame is written */
 int sfb_pipe_stats(sfb_pipe* pipe, uint64_t* frames, uint64_t* bytes);
 int sfb_pipe_close(sfb_pipe* pipe);

@@ -99,6 +99,7 @@ _PROTOTYPES = dict(
     sfb_pipe_open=(c_int, [c_void_p, c_int, c_int, c_size_t, POINTER(c_void_p)]),
     sfb_pipe_acquire=(c_int, [c_void_p, POINTER(c_void_p)]),
     sfb_pipe_submit=(c_int, [c_void_p, c_void_p]),
+    sfb_pipe_set_fd=(c_int, [c_void_p, c_int]),
     sfb_pipe_sync=(c_int, [c_void_p]),
     sfb_pipe_stats=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     sfb_pipe_close=(c_int, [c_void_p]),
@@ -234,7 +235,7 @@ class Texture:
 class Pipe:
     """sfb_pipe handle: device ring + pinned ring + writer thread"""
     def __init__(self, ctx: "Context", fd: int, buffers: int, frame_bytes: int):
-        self.ctx, self.handle, self.frame_bytes = ctx, c_void_p(), frame_bytes
+        self.ctx, self.handle, self.frame_bytes, self.buffers = ctx, c_void_p(), frame_bytes, buffers
         check(lib().sfb_pipe_open(ctx.handle, fd, buffers, frame_bytes, byref(self.handle)))
 
     def acquire(self) -> int:
@@ -247,6 +248,9 @@ class Pipe:
 
     def sync(self) -> None:
         check(lib().sfb_pipe_sync(self.handle))
+
+    def set_fd(self, fd: int) -> None:
+        check(lib().sfb_pipe_set_fd(self.handle, fd))
 
     def stats(self) -> tuple[int, int]:
         f, b = c_uint64(), c_uint64()

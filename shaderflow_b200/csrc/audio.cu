@@ -575,17 +575,9 @@ extern "C" int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_sam
         spec_scan_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(spec_inout_dev, lanes, dt_dev, n_frames, *spec_dynamics);
         SFB_LAUNCH_CHECK(ctx);
     }
-    if (scalars_out_dev) {
-        void* scratch = nullptr;
-        if (int e = sfb_ctx_scratch(ctx, sizeof(float)*2*size_t(n_frames), &scratch)) return e;
-        float* vt = static_cast<float*>(scratch); float* st = vt + n_frames;
-        const int n_last = int(0.1*double(samplerate));           // get_last_n_seconds(0.1): int(n + offset)
-        scalar_targets_kernel<<<n_frames, 256, 0, ctx->stream>>>(pcm_dev, (long long)n_samples, channels,
-            (const long long*)tell_dev, n_frames, n_last, vt, st);
-        SFB_LAUNCH_CHECK(ctx);
-        scalar_scan_kernel<<<1, 32, 0, ctx->stream>>>(vt, st, dt_dev, n_frames, scalars_out_dev);
-        SFB_LAUNCH_CHECK(ctx);
-    }
+    // One scratch request for everything below (per-frame targets + the waveform chunk table): the table
+    // size depends on tell[], which lives on the device, so its two ends are fetched first
+    long long m0 = 0; int n_chunks = 0;
     if (wave_out_dev) {
         SFB_REQUIRE(wave_points > 0 && wave_chunk > 0, "sfb_audio_track: bad waveform shape");
         SFB_REQUIRE(wave_reducer >= 0 && wave_reducer <= 2, "sfb_audio_track: bad reducer %d", wave_reducer);
@@ -594,21 +586,35 @@ extern "C" int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_sam
         SFB_CUDA(cudaMemcpyAsync(&ends[0], tell_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         SFB_CUDA(cudaMemcpyAsync(&ends[1], tell_dev + (n_frames - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         SFB_CUDA(cudaStreamSynchronize(ctx->stream));
-        const long long m0 = ends[0]/wave_chunk - wave_points;
-        const long long m1 = ends[1]/wave_chunk;
-        const int n_chunks = int(m1 - m0);
-        if (n_chunks > 0) {
-            float* table = nullptr;
-            SFB_CUDA(cudaMallocAsync(&table, sizeof(float)*size_t(n_chunks)*channels, ctx->stream));
-            const int warps = n_chunks*channels;
-            waveform_chunks_kernel<<<(warps*32 + 255)/256, 256, 0, ctx->stream>>>(pcm_dev, (long long)n_samples, channels,
-                m0, n_chunks, wave_chunk, wave_reducer, table);
-            SFB_LAUNCH_CHECK(ctx);
-            waveform_gather_kernel<<<n_frames, 256, 0, ctx->stream>>>(table, m0, channels, (const long long*)tell_dev,
-                n_frames, wave_points, wave_chunk, wave_out_dev);
-            SFB_LAUNCH_CHECK(ctx);
-            SFB_CUDA(cudaFreeAsync(table, ctx->stream));
-        }
+        m0 = ends[0]/wave_chunk - wave_points;
+        n_chunks = int(ends[1]/wave_chunk - m0);
+    }
+    const size_t target_floats = scalars_out_dev ? 2*size_t(n_frames) : 0;
+    const size_t table_floats = size_t(n_chunks > 0 ? n_chunks : 0)*size_t(channels);
+    float* scratch = nullptr;
+    if (target_floats + table_floats) {
+        void* raw = nullptr;
+        if (int e = sfb_ctx_scratch(ctx, sizeof(float)*(target_floats + table_floats), &raw)) return e;
+        scratch = static_cast<float*>(raw);
+    }
+    if (scalars_out_dev) {
+        float* vt = scratch; float* st = vt + n_frames;
+        const int n_last = int(0.1*double(samplerate));           // get_last_n_seconds(0.1): int(n + offset)
+        scalar_targets_kernel<<<n_frames, 256, 0, ctx->stream>>>(pcm_dev, (long long)n_samples, channels,
+            (const long long*)tell_dev, n_frames, n_last, vt, st);
+        SFB_LAUNCH_CHECK(ctx);
+        scalar_scan_kernel<<<1, 32, 0, ctx->stream>>>(vt, st, dt_dev, n_frames, scalars_out_dev);
+        SFB_LAUNCH_CHECK(ctx);
+    }
+    if (wave_out_dev && n_chunks > 0) {
+        float* table = scratch + target_floats;
+        const int warps = n_chunks*channels;
+        waveform_chunks_kernel<<<(warps*32 + 255)/256, 256, 0, ctx->stream>>>(pcm_dev, (long long)n_samples, channels,
+            m0, n_chunks, wave_chunk, wave_reducer, table);
+        SFB_LAUNCH_CHECK(ctx);
+        waveform_gather_kernel<<<n_frames, 256, 0, ctx->stream>>>(table, m0, channels, (const long long*)tell_dev,
+            n_frames, wave_points, wave_chunk, wave_out_dev);
+        SFB_LAUNCH_CHECK(ctx);
     }
     return SFB_OK;
 }

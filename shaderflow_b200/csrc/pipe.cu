@@ -123,6 +123,15 @@ extern "C" int sfb_pipe_submit(sfb_pipe* p, const void* frame_dev) {
     return SFB_OK;
 }
 
+extern "C" int sfb_pipe_set_fd(sfb_pipe* p, int fd) {
+    SFB_REQUIRE(p, "sfb_pipe_set_fd: null pipe");
+    std::unique_lock<std::mutex> lock(p->mu);
+    if (p->written != p->submitted || p->acquired)
+        SFB_FAIL(SFB_ESTATE, "sfb_pipe_set_fd: the ring still has frames in flight; call sfb_pipe_sync first");
+    p->fd = fd; p->io_errno = 0;
+    return SFB_OK;
+}
+
 extern "C" int sfb_pipe_sync(sfb_pipe* p) {
     SFB_REQUIRE(p, "sfb_pipe_sync: null pipe");
     std::unique_lock<std::mutex> lock(p->mu);

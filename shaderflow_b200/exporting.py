@@ -134,7 +134,18 @@ class ExportingHelper:
                                                 stdout=self.stdout, stderr=self.stderr)
                 fd = self.process.stdin.fileno()
         self.fileno = fd
-        self.pipe_handle = N.Pipe(self.scene.cuda, fd, max(2, int(self.buffers)), self.frame_bytes)
+        # one ring per scene serves consecutive exports: creating pinned buffers, a stream and a thread per
+        # main() call is measurable on short exports
+        buffers = max(2, int(self.buffers))
+        ring = getattr(self.scene, "_sink_ring", None)
+        if ring is not None and ring.handle and ring.frame_bytes == self.frame_bytes and ring.buffers == buffers:
+            ring.set_fd(fd)
+        else:
+            if ring is not None:
+                ring.close()
+            ring = N.Pipe(self.scene.cuda, fd, buffers, self.frame_bytes)
+            self.scene._sink_ring = ring
+        self.pipe_handle = ring
 
     def make_buffers(self, n: int = 2) -> None:
         self.buffers = n
@@ -162,8 +173,8 @@ class ExportingHelper:
 
     def finish(self) -> None:
         if self.pipe_handle is not None:
-            self.pipe_handle.sync()
-            self.pipe_handle.close()
+            self.pipe_handle.sync()                 # every frame written; the ring itself stays with the scene
+            self.pipe_handle.set_fd(-1)
             self.pipe_handle = None
         if self.process is not None:
             logger.info("Waiting for FFmpeg process to finish encoding")

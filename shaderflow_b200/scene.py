@@ -64,6 +64,8 @@ class ShaderScene(ShaderModule):
     cli: Any = Factory(_Cli)
     fuse: bool = True
     """Use the fused K3+K4 kernel whenever final.glsl degenerates to a box filter"""
+    _sink_ring: Any = None
+    """The frame sink's ring (pinned buffers, copy stream, writer thread), kept across main() calls"""
     kernel_events: Any = None
     """When a list: (start, end) torch CUDA events are appended around every shading launch (bench.py)"""
 
@@ -78,6 +80,10 @@ class ShaderScene(ShaderModule):
                 try: module.destroy()
                 except Exception: pass
         self._frame_buffer = None
+        ring, self._sink_ring = self._sink_ring, None
+        if ring is not None:
+            try: ring.close()
+            except Exception: pass
 
     def initialize(self) -> None:
         if self.shader is not None:

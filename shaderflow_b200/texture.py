@@ -45,10 +45,21 @@ class Anisotropy(Enum):
 
 @define
 class TextureBox:
-    texture: Optional[N.Texture] = None      # libsfb200 texture (sampler + render target)
+    _texture: Optional[N.Texture] = None     # libsfb200 texture (sampler + render target), created on first use
     data: Optional[bytes] = field(default=None, repr=False)
     clear: bool = False
     empty: bool = True
+    factory: Any = field(default=None, repr=False)
+    """() -> N.Texture; render targets that are never sampled or stored (iScreen on the fused path, iFinal)
+    never allocate their 100+ MB of cudaArray + mirror"""
+
+    @property
+    def texture(self) -> Optional[N.Texture]:
+        if self._texture is None and self.factory is not None:
+            self._texture = self.factory()
+            if self.data:
+                self._texture.write(self.data)
+        return self._texture
 
     @property
     def fbo(self) -> Optional[N.Texture]:
@@ -56,9 +67,9 @@ class TextureBox:
         return self.texture
 
     def release(self) -> None:
-        if self.texture is not None:
-            self.texture.destroy()
-            self.texture = None
+        if self._texture is not None:
+            self._texture.destroy()
+            self._texture = None
 
     def __del__(self):
         try: self.release()
@@ -186,19 +197,23 @@ class ShaderTexture(ShaderModule):
         if cuda is None:
             return self
         w, h = self.size
+        signature = (w, h, self.components, str(self.dtype), self.temporal, self.layers)
+        if signature == getattr(self, "_made", None):
+            return self                               # nothing changed: keep the GPU objects (and contents)
+        self._made = signature
         for (_, _, box) in self.boxes:
             box.release()
-            box.texture = N.Texture(cuda, w, h, self.components, _native_dtype(self.dtype),
-                linear=(self.filter is TextureFilter.Linear), repeat_x=self.repeat_x, repeat_y=self.repeat_y)
-            if box.data and (self.size_t == len(box.data)):
-                box.texture.write(box.data)
+            if box.data and (self.size_t != len(box.data)):
+                box.data = None
+            box.factory = (lambda w=w, h=h: N.Texture(cuda, w, h, self.components, _native_dtype(self.dtype),
+                linear=(self.filter is TextureFilter.Linear), repeat_x=self.repeat_x, repeat_y=self.repeat_y))
         self.external = None
         return self
 
     def apply(self) -> "ShaderTexture":
         for (_, _, box) in self.boxes:
-            if box.texture is not None:
-                box.texture.set_sampling(self.filter is TextureFilter.Linear, self.repeat_x, self.repeat_y)
+            if box._texture is not None:                      # lazily created ones pick the state up at creation
+                box._texture.set_sampling(self.filter is TextureFilter.Linear, self.repeat_x, self.repeat_y)
         return self
 
     def destroy(self) -> None:
