@@ -194,6 +194,7 @@ enum {
     SFB_FILTER_HARDWARE = 1,   /* cudaTextureObject filtering (9-bit weights, like GL hardware)       */
     SFB_RENDER_LITERAL = 2,    /* force the literal transliteration of the GLSL (no scene-specific fast  */
                                /* path); the parity anchor the optimised kernels are compared against   */
+    SFB_RENDER_TILED = 4,      /* visualizer: skip the separable kernel, use the per-pixel tiled one      */
 };
 
 /* iScreen pass (K3): one thread per fragment of a target_w x target_h RGBA8 target — replaces

@@ -20,7 +20,7 @@ VOLUME = dict(linear=0, sqrt=1, dbfs=2, dbfs_tremx=3)
 REDUCER = dict(average=0, rms=1, std=2)
 DTYPE_U8, DTYPE_F32, DTYPE_F16 = 0, 1, 2
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
-FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL = 0, 1, 2
+FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL, RENDER_TILED = 0, 1, 2, 4
 SCALARS = 5
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
 

@@ -3,6 +3,7 @@
 // (iFinal / iScreen programs), resources/shaders/fragment/final.glsl.
 #include "scenes.cuh"
 #include "visualizer_tiled.cuh"
+#include "visualizer_rows.h"
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -348,7 +349,13 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
     P.dst = static_cast<unsigned char*>(dst_dev);
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && ssaa <= 4) {
-        // production path of the headline scene: shared-memory window of the background per CTA
+        // production path of the headline scene: the separable kernel when the camera allows it, ...
+        if (!(flags & SFB_RENDER_TILED)) {
+            bool launched = false;
+            if (int e = sfb_visualizer_rows_launch(P, ctx->stream, &launched)) return e;
+            if (launched) { SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
+        }
+        // ... else one thread per output pixel over a shared-memory window of the background
         VisualizerParams VP;
         VP.R = P;
         VP.tmap = background_tensor_map(samplers[0]);

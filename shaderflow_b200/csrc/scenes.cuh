@@ -23,11 +23,11 @@ struct RenderParams {
 struct Frag { vec2 agluv, gluv, astuv, stuv, stxy, glxy; };
 
 // iAspectRatio macro (shaderflow.glsl:16)
-SFB_DEV float aspect_ratio(const sfb_uniforms& u) { return u.iResolution[0]/u.iResolution[1]; }
+SFB_HD float aspect_ratio(const sfb_uniforms& u) { return u.iResolution[0]/u.iResolution[1]; }
 
 // The rasteriser: vertex/default.glsl:8-16 at the quad corners (shader.py:127-128), interpolated
 // affinely (float64) to the centre of fragment (i, j), rounded once — same spec as the oracle.
-SFB_DEV Frag make_frag(const RenderParams& P, int i, int j) {
+SFB_HD Frag make_frag(const RenderParams& P, int i, int j) {
     const double tx = (double(i) + 0.5)*P.inv_Wr, ty = (double(j) + 0.5)*P.inv_Hr;
     const float W = P.u.iResolution[0], H = P.u.iResolution[1];
     const float a = aspect_ratio(P.u);
@@ -52,9 +52,9 @@ struct Camera {
     bool out_of_bounds;
 };
 
-SFB_DEV vec3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+SFB_HD vec3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
 
-SFB_DEV Camera get_camera(const sfb_uniforms& u, const Frag& f) {
+SFB_HD Camera get_camera(const sfb_uniforms& u, const Frag& f) {
     const vec3 pos = ld3(u.iCameraPosition), right = ld3(u.iCameraRight), up = ld3(u.iCameraUpward);
     const vec3 fwd = ld3(u.iCameraForward), back = fwd*(-1.0f);
     const float asp = aspect_ratio(u);

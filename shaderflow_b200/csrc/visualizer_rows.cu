@@ -1,0 +1,473 @@
+// visualizer_rows.cu — separable production kernel of the headline scene (examples/basic/shaders/
+// visualizer.frag fused with fragment/final.glsl), used when the camera is the axis-aligned 2D one every
+// export runs with (camera.py:196-201 defaults: projection 0, right = x, up = y).
+//
+// Under that camera the texel-space position of a fragment's centre tap is SEPARABLE: x depends only on
+// the fragment column, y only on the fragment row (camera.glsl:55-91 + visualizer.frag:16-18 are affine
+// per axis). Every one of the 91 blur taps (visualizer.frag:19-33) adds the same offset to all fragments,
+// so for one tap k
+//     all fragments of a column share (ix, fx)     → the horizontal lerp is done once per column and row
+//     all fragments of a row    share (iy, fy)     → the vertical weights are warp-uniform table entries
+// One thread owns one fragment COLUMN and J consecutive fragment rows. Per tap it
+//   1. computes px, floor, fraction once                                   (4 FP + 3 INT)
+//   2. lerps 4 texel rows horizontally: H_r = T[r][ix] + fx*(T[r][ix+1]-T[r][ix])   (8 LDS + 12 FFMA;
+//      the window holds pre-differenced pair records, so one FFMA per channel)
+//   3. forms the vertical differences D_r = H_{r+1} - H_r                    (9 FADD)
+//   4. for each of its J rows adds  H_0 + sum_r D_r*clamp(py - r0 - r, 0, 1)  — the piecewise-linear
+//      interpolant through H_0..H_3 written with hinge functions, whose three weights come from a
+//      per-CTA shared table indexed (row group, tap, row): 1 broadcast LDS.128 + 9 FFMA per fragment;
+//      H_0 is common to the J rows and is accumulated once.
+// ≈ 15 instructions per (fragment, tap) against ≈ 40 for one-thread-per-fragment bilinear footprints
+// (visualizer_tiled.cuh), and a quarter of its shared-memory wavefronts. Mathematically identical to
+// the bilinear form; float32 re-association only (tests gate it against the literal transliteration).
+//
+// CTA = 64 fragment columns x 4 row groups (256 threads), J = 8 or 4 rows per group chosen by the host
+// from the vertical texel step per fragment (4 texel rows must cover J fragment rows). The background
+// window (64 x win_h texels) is staged by TMA bulk copies (cp.async.bulk, one 256-byte row each, mbarrier
+// complete_tx) when it lies inside the texture, by wrapped loads at the edges. CTAs whose geometry does
+// not fit (window too large, NaN) shade through the per-tap global path, like the tiled kernel.
+#include "scenes.cuh"
+#include "visualizer_tiled.cuh"
+#include "visualizer_rows.h"
+
+#include <math.h>
+
+namespace glsl {
+
+constexpr int VR_COLS = 64;            // fragment columns per CTA (threadIdx.x)
+constexpr int VR_GROUPS = 4;           // row groups per CTA (threadIdx.y)
+constexpr int VR_THREADS = VR_COLS*VR_GROUPS;
+constexpr int VR_WIN_W = 64;           // window row stride, texels
+constexpr int VR_MAX_H = 40;           // window rows the launcher may ask for
+constexpr int VR_TAPS = 81;            // 10 (ray 0, weighted twice) + 70 (rays 1-7) + 1 (undisplaced)
+constexpr int VR_ROWS = 4;             // texel rows interpolated per tap: covers a vertical span < 2 texels
+
+struct RowsTaps { float dx[VR_TAPS + 3]; float dy[VR_TAPS + 3]; };
+__constant__ RowsTaps c_rows;
+
+struct VisRowsParams {
+    RenderParams R;
+    int win_h;                         // window rows staged (dynamic shared memory is sized for it)
+    int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
+};
+
+SFB_DEV void bulk_load_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// pow(x, y) for x >= 0 through exp2f(y*log2f(x)) (libdevice, <= 2 ulp each): the exponents used here are
+// <= 0.5 in magnitude, which shrinks the relative error of log2f; pow(0, y > 0) = 0 like powf
+SFB_DEV float pow_pos(float x, float y) { return exp2f(y*log2f(x)); }
+
+// Per-frame constants of visualizer.frag:35-73 (functions of the uniforms only)
+struct BackConsts { float std5, mscale, vexp; };
+
+// Everything of main() after the blur loop (visualizer.frag:35-73) for the separable camera: the column
+// gives (agluv.x, astuv.x, uv.x, waveform thresholds), the row gives (agluv.y, astuv.y, uv.y). Same
+// mathematics and operation order as vis_back (visualizer_tiled.cuh); pow with a constant exponent 6 is
+// three multiplies, the fractional powers go through pow_pos, divisions by constants are multiplications.
+SFB_DEV vec3 vis_back_sep(const RenderParams& P, const BackConsts& K, vec3 rgb, float agx, float asx, float uvx,
+                          float wavx, float wavy, float agy, float asy, float uvy) {
+    const vec3 space = mk3(1.0f, 11.0f, 26.0f)/255.0f;
+    const float t = clamp(sqrtf(agx*agx + agy*agy) - 0.3f, 0.0f, 1.0f), t2 = t*t;
+    rgb = rgb*(1.0f + K.std5*(t2*t2*t2));
+    const float c = -4.37113883e-08f, sn = -1.0f;                 // cos, sin of float32(-PI/2)
+    const float mx = (c*uvx + sn*uvy)*K.mscale, my = ((-sn)*uvx + c*uvy)*K.mscale;
+    const float radius = 0.17f;
+    const float circle = fabsf(atan2f(my, mx)*(1.0f/PI));
+    // texture(iSpectrogram, (0, circle)): NEAREST on an RG32F column (spectrogram.py:272-282)
+    const DevSampler& sp = P.tex[1];
+    float2 sv;
+    if (sp.dtype == SFB_DTYPE_F32 && sp.padded == 2 && sp.w == 1 && sp.filter == SFB_FILTER_NEAREST) {
+        sv = __ldg(reinterpret_cast<const float2*>(sp.lin) + wrap_index(int(floorf(circle*float(sp.h))), sp.h, sp.ry));
+    } else {
+        const vec4 q = texture<false>(sp, mk2(0.0f, circle)); sv = make_float2(q.x, q.y);
+    }
+    const float h = clamp(circle*0.5f, 0.0f, 1.0f);
+    const float fscale = 0.05f + 3.0f*(h*h*(3.0f - 2.0f*h));
+    const float lm = sqrtf(mx*mx + my*my);
+    if (lm < radius) {
+        rgb = rgb*0.5f;
+    } else {
+        const float bar = sqrtf(((my < 0.0f) ? sv.x : sv.y)*0.001f)*fscale;
+        const float r = radius + 0.5f*bar;
+        if (lm < r) { const float g = clamp(0.5f + bar, 0.0f, 1.0f); rgb = mix(rgb, mk3(1.0f), g*g*(3.0f - 2.0f*g)); }
+        else        rgb = rgb*pow_pos((lm - r)*0.5f, 0.05f);
+    }
+    { const float g = clamp(sqrtf(uvx*uvx + uvy*uvy)*0.05f, 0.0f, 1.0f); rgb = mix(rgb, space, g*g*(3.0f - 2.0f*g)); }
+    rgb = rgb*pow_pos((asx*(1.0f - asy))*(asy*(1.0f - asx))*20.0f, K.vexp);
+    if (1.0f - agy < wavx) rgb = rgb*0.8f;
+    if (1.0f + agy < wavy) rgb = rgb*0.8f;
+    return rgb;
+}
+
+// The per-tap global path for CTAs whose geometry does not fit; kept out of line (it is cold and large)
+__device__ __noinline__ void visualizer_unfitted(const RenderParams& P, int i, int j, float* rgb) {
+    const vec4 c = scene_visualizer_fast(P, make_frag(P, i, j));
+    rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
+}
+
+template <int S, int J>
+__global__ void __launch_bounds__(VR_THREADS, 2)
+visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
+    static_assert(J % S == 0 && VR_COLS % S == 0, "a CTA shades whole output pixels");
+    const RenderParams& P = VP.R;
+    const int win_h = VP.win_h;
+    extern __shared__ __align__(128) unsigned char vr_smem[];
+    float4* rg = reinterpret_cast<float4*>(vr_smem);                                     // [win_h][64] (r, g, r'-r, g'-g)
+    float2* bb = reinterpret_cast<float2*>(vr_smem + sizeof(float4)*VR_WIN_W*win_h);     // [win_h][64] (b, b'-b)
+    float4* tbl = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][81][J]
+    __shared__ float red[2][VR_THREADS/32];
+    __shared__ float cyS[VR_GROUPS][J];
+    __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
+    __shared__ int win[5];                                                               // x0, y0, fits, tma, table overflow
+    __shared__ __align__(8) unsigned long long bar;
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty*VR_COLS + tx;
+    const int i = blockIdx.x*VR_COLS + tx;                        // fragment column
+    const int jb = blockIdx.y*(VR_GROUPS*J) + ty*J;               // first fragment row of this thread
+    const DevSampler& bg = P.tex[0];
+    const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
+    const float iTime = P.u.iTime, iAudioVolume = P.u.extra[0][0];
+    const float zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*iAudioVolume - 0.03f;
+    const vec2 wobble = 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
+    const float intensity = 0.01f*clamp(powf(iAudioVolume, 2.5f), 0.0f, 0.3f);
+    const float scale = intensity*fh;                             // st displacement → texels (hw*fw == fh)
+
+    // ---- A. centre-tap positions: x per column, y per row (coordinates clamped onto the target) ----
+    const int ic = min(i, P.Wr - 1), jc = min(jb, P.Hr - 1);
+    const VisFrag vc = vis_front(P, ic, jc, fw, fh, hw, wobble, zf);
+    const float tapx = vc.tap.x;
+    if (tx < J) {
+        const VisFrag vr = vis_front(P, min(int(blockIdx.x)*VR_COLS, P.Wr - 1), min(jb + tx, P.Hr - 1), fw, fh, hw, wobble, zf);
+        cyS[ty][tx] = vr.tap.y;
+        rowS[ty][tx] = make_float4(vr.f.agluv.y, vr.f.astuv.y, vr.uv.y, 0.0f);
+    }
+    {
+        float lo = tapx, hi = tapx;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = lo; red[1][tid >> 5] = hi; }
+    }
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        float ax = red[0][0], bx = red[1][0], ay = cyS[0][0], by = cyS[0][0];
+        for (int w = 1; w < VR_THREADS/32; w++) { ax = fminf(ax, red[0][w]); bx = fmaxf(bx, red[1][w]); }
+        for (int g = 0; g < VR_GROUPS; g++)
+            for (int r = 0; r < J; r++) { ay = fminf(ay, cyS[g][r]); by = fmaxf(by, cyS[g][r]); }
+        const float reach = scale*1.0001f + 1.0f;                 // |dir*walk| <= 1.0000001; +1 keeps local coords >= 1
+        // bulk copies need 16-byte aligned rows: x0 % 4 == 0
+        const int x0 = (int(floorf(ax - reach)) - 1) & ~3, y0 = int(floorf(ay - reach)) - 1;
+        const int x1 = int(floorf(bx + reach)) + 2, y1 = int(floorf(by + reach)) + 2;    // last texel touched + 1
+        const bool finite = (ax == ax) && (bx == bx) && (ay == ay) && (by == by) && fabsf(ax) < 1.0e9f && fabsf(bx) < 1.0e9f
+                         && fabsf(ay) < 1.0e9f && fabsf(by) < 1.0e9f;
+        win[0] = x0; win[1] = y0; win[4] = 0;
+        // pair records need texel x+1: the last window column only ever serves as a neighbour
+        win[2] = (finite && (x1 - x0) <= VR_WIN_W - 1 && (y1 - y0) <= win_h) ? 1 : 0;
+        win[3] = (win[2] && (bg.w % 4) == 0 && x0 >= 0 && y0 >= 0 && x0 + VR_WIN_W <= bg.w && y0 + win_h <= bg.h) ? 1 : 0;
+        if (win[3]) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar, VR_WIN_W*4*win_h);
+        }
+    }
+    __syncthreads();
+    const int x0 = win[0], y0 = win[1];
+    const bool window_ok = win[2] != 0, tma = win[3] != 0;
+
+    // ---- B1. TMA: raw RGBA8 rows land at the start of the window buffer (256 B per row) -------------
+    if (tma && tid < win_h) {
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(bg.lin) + size_t(y0 + tid)*size_t(bg.w) + size_t(x0);
+        bulk_load_row(vr_smem + tid*(VR_WIN_W*4), src, VR_WIN_W*4, &bar);
+    }
+
+    // ---- C. vertical table: hinge weights of every (row group, tap, row), warp-uniform in the main loop
+    if (window_ok) {
+        const float y0f = float(y0);
+        int bad = 0;
+        for (int e = tid; e < VR_GROUPS*VR_TAPS*J; e += VR_THREADS) {
+            const int g = e/(VR_TAPS*J), rem = e - g*(VR_TAPS*J), k = rem/J, r = rem - k*J;
+            const float dy = c_rows.dy[k];
+            const float p0 = fmaf(dy, scale, cyS[g][0] - y0f), pl = fmaf(dy, scale, cyS[g][J - 1] - y0f);
+            const float py = fmaf(dy, scale, cyS[g][r] - y0f);
+            const float r0f = floorf(fminf(p0, pl));
+            const float t = py - r0f;
+            const int r0 = int(r0f);
+            if (!(t >= 0.0f && t <= float(VR_ROWS - 1)) || r0 < 0 || r0 + VR_ROWS > win_h) bad = 1;
+            // byte offset of window row r0 in the (b, b'-b) plane, with the 2^23 exponent bits of the magic
+            // floor of x folded in (modulo 2^32); the (r, g) plane uses twice this offset
+            const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
+            tbl[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+        }
+        if (bad) win[4] = 1;                                       // benign race: every writer stores 1
+    }
+
+    // ---- B2. widen the window into pre-differenced pair records -------------------------------------
+    if (window_ok) {
+        constexpr int PER = (VR_WIN_W*VR_MAX_H + VR_THREADS - 1)/VR_THREADS;
+        unsigned int w0[PER], w1[PER];
+        const int n = VR_WIN_W*win_h;
+        if (tma) {
+            mbar_wait(&bar, 0);
+            const unsigned int* raw = reinterpret_cast<const unsigned int*>(vr_smem);
+            #pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int t = tid + k*VR_THREADS;
+                if (t < n) { w0[k] = raw[t]; w1[k] = raw[((t % VR_WIN_W) == VR_WIN_W - 1) ? t : t + 1]; }
+            }
+        } else {
+            const unsigned int* texels = reinterpret_cast<const unsigned int*>(bg.lin);
+            #pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int t = tid + k*VR_THREADS;
+                if (t < n) {
+                    const int gy = wrap_index(y0 + (t / VR_WIN_W), bg.h, bg.ry);
+                    const unsigned int* row = texels + size_t(gy)*size_t(bg.w);
+                    w0[k] = __ldg(row + wrap_index(x0 + (t % VR_WIN_W), bg.w, bg.rx));
+                    w1[k] = __ldg(row + wrap_index(x0 + (t % VR_WIN_W) + 1, bg.w, bg.rx));
+                }
+            }
+        }
+        __syncthreads();                                           // raw rows fully read before they are overwritten
+        #pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int t = tid + k*VR_THREADS;
+            if (t < n) {
+                const vec3 a = widen3(w0[k]), b = widen3(w1[k]);
+                rg[t] = make_float4(a.x, a.y, b.x - a.x, b.y - a.y);
+                bb[t] = make_float2(a.z, b.z - a.z);
+            }
+        }
+    }
+    __syncthreads();
+    const bool fits = window_ok && win[4] == 0;
+
+    // ---- D. blur: taps x rows -----------------------------------------------------------------------
+    float base0 = 0.0f, base1 = 0.0f, base2 = 0.0f;
+    float acc[J][3];
+    #pragma unroll
+    for (int r = 0; r < J; r++) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; }
+    if (fits && !(VP.debug & 1)) {
+        const float cx = tapx - float(x0);                         // tile-local, >= 1 by construction of x0
+        const char* rgB = reinterpret_cast<const char*>(rg);
+        const char* bbB = reinterpret_cast<const char*>(bb);
+        const float4* T = tbl + ty*(VR_TAPS*J);
+        auto tap = [&](int k) {
+            const float4 e0 = T[k*J];
+            const float px = fmaf(c_rows.dx[k], scale, cx);
+            // floor for 0.5 <= p < 2^22: p + (2^23 - 0.5) rounds to floor(p) + 2^23 (ties land on either
+            // neighbour; the interpolant is continuous there)
+            const float tx_ = px + 8388607.5f;
+            const float a = px - (tx_ - 8388608.0f);
+            const unsigned int off8 = __float_as_uint(e0.w) + (__float_as_uint(tx_) << 3);
+            const char* pr = rgB + 2u*off8;
+            const char* pb = bbB + off8;
+            float H[VR_ROWS][3];
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS; r++) {
+                const float4 q = *reinterpret_cast<const float4*>(pr + r*(VR_WIN_W*16));
+                const float2 s = *reinterpret_cast<const float2*>(pb + r*(VR_WIN_W*8));
+                H[r][0] = fmaf(a, q.z, q.x); H[r][1] = fmaf(a, q.w, q.y); H[r][2] = fmaf(a, s.y, s.x);
+            }
+            base0 += H[0][0]; base1 += H[0][1]; base2 += H[0][2];
+            float D[VR_ROWS - 1][3];
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS - 1; r++) {
+                D[r][0] = H[r + 1][0] - H[r][0]; D[r][1] = H[r + 1][1] - H[r][1]; D[r][2] = H[r + 1][2] - H[r][2];
+            }
+            #pragma unroll
+            for (int r = 0; r < J; r++) {
+                const float4 e = (r == 0) ? e0 : T[k*J + r];
+                #pragma unroll
+                for (int c = 0; c < 3; c++)
+                    acc[r][c] = fmaf(e.x, D[0][c], fmaf(e.y, D[1][c], fmaf(e.z, D[2][c], acc[r][c])));
+            }
+        };
+        // ray 0 (angle 0) stands for itself and for the 9th float-loop direction (visualizer_tiled.cuh): weight 2
+        #pragma unroll 2
+        for (int k = 0; k < 10; k++) tap(k);
+        base0 += base0; base1 += base1; base2 += base2;
+        #pragma unroll
+        for (int r = 0; r < J; r++) { acc[r][0] += acc[r][0]; acc[r][1] += acc[r][1]; acc[r][2] += acc[r][2]; }
+        #pragma unroll 2
+        for (int k = 10; k < VR_TAPS; k++) tap(k);
+    }
+
+    // ---- E. rest of main() per fragment, 8-bit store rule per sub-sample, box sum --------------------
+    // The blurred colours go through shared memory so that the back end is ONE rolled loop (unrolled J
+    // times it overflows the instruction cache: ncu showed 2.3 no-instruction stalls per issue).
+    __syncthreads();                                               // table and window are dead: reuse them
+    float4* stash = reinterpret_cast<float4*>(vr_smem);            // [J][256] blurred rgb, each thread reads its own
+    unsigned char* stage = vr_smem + sizeof(float4)*J*VR_THREADS;  // rgb24 rows of the CTA
+    {
+        const float norm = (1.0f/255.0f)/(10.0f*8.0f);
+        #pragma unroll
+        for (int r = 0; r < J; r++)
+            stash[r*VR_THREADS + tid] = make_float4((base0 + acc[r][0])*norm, (base1 + acc[r][1])*norm, (base2 + acc[r][2])*norm, 0.0f);
+    }
+    constexpr int PX = VR_COLS/S;                                  // output pixels per CTA row
+    constexpr int RB = PX*3;                                       // staged bytes per output row
+    const bool col_in = i < P.Wr;
+    const bool words = (P.comps == 3) && (P.W % 4 == 0) && (int(blockIdx.x)*PX + PX <= P.W);
+    BackConsts K;
+    K.std5 = 5.0f*P.u.extra[1][0];
+    K.mscale = 1.0f - 0.4f*powf(fabsf(iAudioVolume), 0.5f);
+    K.vexp = 0.1f + 0.15f*iAudioVolume;
+    const float agx = vc.f.agluv.x, asx = vc.f.astuv.x, uvx = vc.uv.x;
+    float wavx, wavy;
+    { const vec4 w = texture<false>(P.tex[2], mk2(asx, 0.0f)); wavx = 0.2f*w.x; wavy = 0.2f*w.y; }
+    #pragma unroll 1
+    for (int pr = 0; pr < J/S; pr++) {
+        unsigned int r8 = 0, g8 = 0, b8 = 0;
+        #pragma unroll 1
+        for (int s = 0; s < S; s++) {
+            const int r = pr*S + s;
+            vec3 c;
+            if (vc.oob) {
+                c = mk3(1.0f, 11.0f, 26.0f)/255.0f;
+            } else if (!fits) {                                    // geometry did not fit: per-tap global path
+                float q[3]; visualizer_unfitted(P, ic, min(jb + r, P.Hr - 1), q); c = mk3(q[0], q[1], q[2]);
+            } else {
+                const float4 q = stash[r*VR_THREADS + tid];
+                const float4 row = rowS[ty][r];
+                c = (VP.debug & 2) ? mk3(q.x, q.y, q.z)
+                                   : vis_back_sep(P, K, mk3(q.x, q.y, q.z), agx, asx, uvx, wavx, wavy, row.x, row.y, row.z);
+            }
+            r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
+            g8 += (unsigned int)__float2int_rn(__saturatef(c.y)*255.0f);
+            b8 += (unsigned int)__float2int_rn(__saturatef(c.z)*255.0f);
+        }
+        #pragma unroll
+        for (int o = 1; o < S; o <<= 1) {
+            r8 += __shfl_xor_sync(0xffffffffu, r8, o); g8 += __shfl_xor_sync(0xffffffffu, g8, o); b8 += __shfl_xor_sync(0xffffffffu, b8, o);
+        }
+        const float inv = 1.0f/float(S*S);
+        r8 = (unsigned int)__float2int_rn(float(r8)*inv);
+        g8 = (unsigned int)__float2int_rn(float(g8)*inv);
+        b8 = (unsigned int)__float2int_rn(float(b8)*inv);
+        const int y = (jb + pr*S)/S, x = i/S;                      // output pixel
+        if ((tx % S) == 0 && col_in && y < P.H) {
+            if (P.comps == 4) {
+                reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
+            } else if (!words) {
+                unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r8; p[1] = g8; p[2] = b8;
+            } else {
+                unsigned char* p = stage + ((ty*J)/S + pr)*RB + (tx/S)*3; p[0] = r8; p[1] = g8; p[2] = b8;
+            }
+        }
+    }
+    if (!words) return;
+    __syncthreads();
+    constexpr int ROWS_OUT = VR_GROUPS*J/S, WPR = RB/4;            // staged rows, 32-bit words per row
+    for (int e = tid; e < ROWS_OUT*WPR; e += VR_THREADS) {
+        const int row = e/WPR, wc = e - row*WPR;
+        const int y = blockIdx.y*ROWS_OUT + row;
+        if (y < P.H) {
+            unsigned int* out = reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(blockIdx.x)*PX)*3);
+            out[wc] = reinterpret_cast<const unsigned int*>(stage)[e];
+        }
+    }
+}
+
+} // namespace glsl
+
+using namespace glsl;
+
+// Tap offsets dir*walk of visualizer.frag:26-27, evaluated in strict float32 on the host exactly like
+// render.cu's build_blur_table (9 angles x 10 walks; the 9th direction coincides with the first and is
+// folded into it). Order: ray 0 (10), rays 1-7 (70), the undisplaced first tap. Both constant tables of
+// this translation unit are filled: the per-tap global path reads c_blur.
+static int build_rows_tables() {
+    static bool done[64] = {};
+    int device = 0;
+    SFB_CUDA(cudaGetDevice(&device));
+    if (device < 64 && done[device]) return SFB_OK;
+    BlurTable blur;
+    RowsTaps rows;
+    memset(&rows, 0, sizeof(rows));
+    const volatile float TAU_F = 6.2831853071795864f, directions = 8.0f, quality = 10.0f;
+    int n = 0;
+    for (volatile float angle = 0.0f; angle < TAU_F; angle = angle + TAU_F/directions) {
+        const float c = cosf(angle), s = sinf(angle);
+        for (volatile float walk = 1.0f/quality; walk <= 1.001f; walk = walk + 1.0f/quality) {
+            if (n >= 90) SFB_FAIL(SFB_ESTATE, "blur table overflow: float loop semantics changed");
+            blur.tap[n++] = make_float2(c*walk, s*walk);
+        }
+    }
+    if (n != 90) SFB_FAIL(SFB_ESTATE, "blur table has %d taps, expected 90", n);
+    blur.tap[90] = make_float2(0.0f, 0.0f); blur.tap[91] = make_float2(0.0f, 0.0f);
+    for (int k = 0; k < 80; k++) { rows.dx[k] = blur.tap[k].x; rows.dy[k] = blur.tap[k].y; }
+    rows.dx[80] = 0.0f; rows.dy[80] = 0.0f;
+    SFB_CUDA(cudaMemcpyToSymbol(c_blur, &blur, sizeof(blur)));
+    SFB_CUDA(cudaMemcpyToSymbol(c_rows, &rows, sizeof(rows)));
+    if (device < 64) done[device] = true;
+    return SFB_OK;
+}
+
+template <int S, int J> static cudaError_t launch_rows(const VisRowsParams& VP, cudaStream_t st) {
+    static bool configured = false;
+    const size_t table = sizeof(float4)*VR_GROUPS*VR_TAPS*J;
+    if (!configured) {
+        const size_t most = (sizeof(float4) + sizeof(float2))*VR_WIN_W*VR_MAX_H + table;
+        cudaError_t e = cudaFuncSetAttribute(visualizer_rows_kernel<S, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
+    dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
+    visualizer_rows_kernel<S, J><<<grid, block, smem, st>>>(VP);
+    return cudaSuccess;
+}
+
+// Launch planning on the host: the same vis_front the kernel evaluates gives the texel step per fragment.
+int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, bool* launched) {
+    *launched = false;
+    static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
+    if (disabled) return SFB_OK;
+    const sfb_uniforms& u = P.u;
+    const int S = P.ssaa;
+    if (!(S == 1 || S == 2 || S == 4)) return SFB_OK;
+    // separable camera: 2D ray through the z = 1 plane with the canonical basis (camera.glsl:55-91)
+    const bool canonical = u.iCameraProjection == 0
+        && u.iCameraRight[0] == 1.0f && u.iCameraRight[1] == 0.0f && u.iCameraRight[2] == 0.0f
+        && u.iCameraUpward[0] == 0.0f && u.iCameraUpward[1] == 1.0f && u.iCameraUpward[2] == 0.0f;
+    if (!canonical || P.Wr < 2 || P.Hr < 2) return SFB_OK;
+    const DevSampler& bg = P.tex[0];
+    const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
+    const float iTime = u.iTime, vol = u.extra[0][0];
+    const float zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*vol - 0.03f;
+    const vec2 wobble = 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
+    const float scale = 0.01f*fminf(fmaxf(powf(vol, 2.5f), 0.0f), 0.3f)*fh;
+    const vec2 t00 = vis_front(P, 0, 0, fw, fh, hw, wobble, zf).tap;
+    const vec2 t10 = vis_front(P, P.Wr - 1, 0, fw, fh, hw, wobble, zf).tap;
+    const vec2 t01 = vis_front(P, 0, P.Hr - 1, fw, fh, hw, wobble, zf).tap;
+    const double sx = fabs(double(t10.x) - double(t00.x))/double(P.Wr - 1);
+    const double sy = fabs(double(t01.y) - double(t00.y))/double(P.Hr - 1);
+    if (!(sx == sx && sy == sy && scale == scale) || !(sx < 1e6 && sy < 1e6 && scale < 1e6)) return SFB_OK;
+    if (t10.y != t00.y || t01.x != t00.x) return SFB_OK;               // not separable after all
+    int J;
+    if (7.0*sy <= 1.9 && 8 % S == 0) J = 8;
+    else if (3.0*sy <= 1.9 && 4 % S == 0) J = 4;
+    else return SFB_OK;
+    const double reach = double(scale)*1.0001 + 1.0;
+    if ((VR_COLS - 1)*sx + 2.0*reach + 9.0 > double(VR_WIN_W - 1)) return SFB_OK;
+    const int win_h = int(ceil((VR_GROUPS*J - 1)*sy + 2.0*reach)) + 7;
+    if (win_h > VR_MAX_H) return SFB_OK;
+    if (int e = build_rows_tables()) return e;
+    VisRowsParams VP;
+    VP.R = P; VP.win_h = win_h;
+    static const int debug = getenv("SFB_ROWS_DEBUG") ? atoi(getenv("SFB_ROWS_DEBUG")) : 0;
+    VP.debug = debug;
+    cudaError_t e = cudaSuccess;
+    if (J == 8) {
+        if (S == 1) e = launch_rows<1, 8>(VP, stream); else if (S == 2) e = launch_rows<2, 8>(VP, stream); else e = launch_rows<4, 8>(VP, stream);
+    } else {
+        if (S == 1) e = launch_rows<1, 4>(VP, stream); else if (S == 2) e = launch_rows<2, 4>(VP, stream); else e = launch_rows<4, 4>(VP, stream);
+    }
+    SFB_CUDA(e);
+    *launched = true;
+    return SFB_OK;
+}

@@ -1,0 +1,9 @@
+// visualizer_rows.h — entry of the separable visualizer kernel (visualizer_rows.cu), called by
+// sfb_render_frame (render.cu). Not part of the ABI.
+#pragma once
+#include "scenes.cuh"
+
+// Plans and launches the separable kernel when the frame qualifies (axis-aligned 2D camera, ssaa 1/2/4,
+// vertical texel step small enough, window fits); *launched says whether it did. P must be fully filled
+// (fill_params + geometry) with P.fast set.
+int sfb_visualizer_rows_launch(const glsl::RenderParams& P, cudaStream_t stream, bool* launched);

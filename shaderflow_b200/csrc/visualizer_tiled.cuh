@@ -68,7 +68,7 @@ SFB_DEV void tma_load_2d(void* dst, const void* tmap, unsigned long long* bar, i
 // (u*W - 0.5, v*H - 0.5), shaderflow.glsl:165-169,202-204 applied to visualizer.frag:16-18
 struct VisFrag { Frag f; vec2 uv; vec2 tap; bool oob; };
 
-SFB_DEV VisFrag vis_front(const RenderParams& P, int i, int j, float fw, float fh, float hw, vec2 wobble, float zf) {
+SFB_HD VisFrag vis_front(const RenderParams& P, int i, int j, float fw, float fh, float hw, vec2 wobble, float zf) {
     VisFrag v;
     v.f = make_frag(P, i, j);
     Camera cam = get_camera(P.u, v.f);

@@ -1,64 +1,76 @@
-// Microbenchmark: issue rate of FFMA vs fma.rn.f32x2 (FFMA2) vs FADD on sm_100a
+// Microbenchmark: issue rate of FFMA vs fma.rn.f32x2 (FFMA2, vector and scalar-broadcast operands) on sm_100a
 #include <cstdio>
 #include <cuda_runtime.h>
 #define ITERS 4096
 __global__ void k_ffma(float* out, float a, float b) {
-    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0+4, x5=x0+5, x6=x0+6, x7=x0+7;
+    float x[16];
+    for (int k = 0; k < 16; k++) x[k] = threadIdx.x + k;
     for (int i = 0; i < ITERS; i++) {
-        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
-        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        #pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = fmaf(x[k], a, b);
     }
-    out[blockIdx.x*blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    float s = 0; for (int k = 0; k < 16; k++) s += x[k];
+    out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
-__global__ void k_ffma2(float* out, float a, float b) {
-    unsigned long long x0, x1, x2, x3, x4, x5, x6, x7, A, B;
-    float f = threadIdx.x;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(f), "f"(f + 1)); x1 = x0; x2 = x0; x3 = x0; x4=x0;x5=x0;x6=x0;x7=x0;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(A) : "f"(a));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+__device__ __forceinline__ unsigned long long pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 unpack(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+// 8 independent pair chains = the same 16 float chains as k_ffma
+__global__ void k_ffma2(float* out, float a, float a2, float b, float b2) {
+    unsigned long long x[8];
+    for (int k = 0; k < 8; k++) x[k] = pack(threadIdx.x + 2*k, threadIdx.x + 2*k + 1);
+    const unsigned long long A = pack(a, a2), B = pack(b, b2);
     for (int i = 0; i < ITERS; i++) {
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x0) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x1) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x2) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x3) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x4) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x5) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x6) : "l"(A), "l"(B));
-        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x7) : "l"(A), "l"(B));
+        #pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[k]) : "l"(A), "l"(B));
     }
-    float lo, hi; unsigned long long s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s));
-    out[blockIdx.x*blockDim.x + threadIdx.x] = lo + hi;
+    float s = 0; for (int k = 0; k < 8; k++) { float2 v = unpack(x[k]); s += v.x + v.y; }
+    out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
-__global__ void k_fadd(float* out, float a, float b) {
-    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0+4, x5=x0+5, x6=x0+6, x7=x0+7;
+// scalar-broadcast multiplier (both halves from one register)
+__global__ void k_ffma2s(float* out, float a, float b, float b2) {
+    unsigned long long x[8];
+    for (int k = 0; k < 8; k++) x[k] = pack(threadIdx.x + 2*k, threadIdx.x + 2*k + 1);
+    const unsigned long long A = pack(a, a), B = pack(b, b2);
     for (int i = 0; i < ITERS; i++) {
-        x0 = __fadd_rn(x0, a); x1 = __fadd_rn(x1, a); x2 = __fadd_rn(x2, a); x3 = __fadd_rn(x3, a);
-        x4 = __fadd_rn(x4, a); x5 = __fadd_rn(x5, a); x6 = __fadd_rn(x6, a); x7 = __fadd_rn(x7, a);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[k]) : "l"(A), "l"(B));
     }
-    out[blockIdx.x*blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    float s = 0; for (int k = 0; k < 8; k++) { float2 v = unpack(x[k]); s += v.x + v.y; }
+    out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
-__global__ void k_mix(float* out, float a, float b) {   // FFMA + integer LOP3 interleaved
-    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3; unsigned y0 = threadIdx.x, y1 = y0*3, y2 = y0*5, y3 = y0*7;
+// 8 FFMA2 + 8 broadcast LDS.128 per iteration (the visualizer's table loads riding along)
+__global__ void k_ffma2_lds(float* out, float a, float a2, float b, float b2) {
+    __shared__ float4 tab[256];
+    tab[threadIdx.x] = make_float4(a, a2, b, b2);
+    __syncthreads();
+    unsigned long long x[8];
+    for (int k = 0; k < 8; k++) x[k] = pack(threadIdx.x + 2*k, threadIdx.x + 2*k + 1);
     for (int i = 0; i < ITERS; i++) {
-        x0 = fmaf(x0, a, b); y0 = (y0 ^ 0x9e3779b9u) + (y0 << 3); x1 = fmaf(x1, a, b); y1 = (y1 ^ 0x9e3779b9u) + (y1 << 3);
-        x2 = fmaf(x2, a, b); y2 = (y2 ^ 0x9e3779b9u) + (y2 << 3); x3 = fmaf(x3, a, b); y3 = (y3 ^ 0x9e3779b9u) + (y3 << 3);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 t = tab[(i*8 + k) & 255];
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[k]) : "l"(pack(t.x, t.y)), "l"(pack(t.z, t.w)));
+        }
     }
-    out[blockIdx.x*blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + float(y0 ^ y1 ^ y2 ^ y3);
+    float s = 0; for (int k = 0; k < 8; k++) { float2 v = unpack(x[k]); s += v.x + v.y; }
+    out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
-template <typename K> float run(K k, float* out) {
+template <typename F> float run(F launch) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    k<<<148*8, 256>>>(out, 1.0001f, 0.5f); cudaDeviceSynchronize();
-    cudaEventRecord(a); k<<<148*8, 256>>>(out, 1.0001f, 0.5f); cudaEventRecord(b); cudaEventSynchronize(b);
+    launch(); cudaDeviceSynchronize();
+    cudaEventRecord(a); launch(); cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b); return ms;
 }
 int main() {
     float* out; cudaMalloc(&out, 148*8*256*4);
-    double n = 148.0*8*256*ITERS*8;
-    float t1 = run(k_ffma, out), t2 = run(k_ffma2, out), t3 = run(k_fadd, out), t4 = run(k_mix, out);
-    printf("FFMA : %.3f ms  %.1f Tinstr-lanes/s (%.1f TFLOP/s)\n", t1, n/t1/1e9, 2*n/t1/1e9);
-    printf("FFMA2: %.3f ms  %.1f Tinstr-lanes/s (%.1f TFLOP/s)\n", t2, n/t2/1e9, 4*n/t2/1e9);
-    printf("FADD : %.3f ms  %.1f Tinstr-lanes/s\n", t3, n/t3/1e9);
-    printf("MIX  : %.3f ms  (4 FFMA + 4x3 int per iter)\n", t4);
+    const double fma = 148.0*8*256*ITERS*16;      // scalar FMAs per launch, every kernel
+    float t1 = run([&]{ k_ffma<<<148*8, 256>>>(out, 1.0001f, 0.5f); });
+    float t2 = run([&]{ k_ffma2<<<148*8, 256>>>(out, 1.0001f, 1.0002f, 0.5f, 0.25f); });
+    float t3 = run([&]{ k_ffma2s<<<148*8, 256>>>(out, 1.0001f, 0.5f, 0.25f); });
+    float t4 = run([&]{ k_ffma2_lds<<<148*8, 256>>>(out, 1.0001f, 1.0002f, 0.5f, 0.25f); });
+    printf("FFMA      : %.3f ms  %.1f TFLOP/s\n", t1, 2*fma/t1/1e9);
+    printf("FFMA2     : %.3f ms  %.1f TFLOP/s\n", t2, 2*fma/t2/1e9);
+    printf("FFMA2 bcst: %.3f ms  %.1f TFLOP/s\n", t3, 2*fma/t3/1e9);
+    printf("FFMA2+LDS : %.3f ms  %.1f TFLOP/s (8 FFMA2 + 8 broadcast LDS.128 per iteration)\n", t4, 2*fma/t4/1e9);
     return 0;
 }
