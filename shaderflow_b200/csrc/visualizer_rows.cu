@@ -5,21 +5,28 @@
 // Under that camera the texel-space position of a fragment's centre tap is SEPARABLE: x depends only on
 // the fragment column, y only on the fragment row (camera.glsl:55-91 + visualizer.frag:16-18 are affine
 // per axis). Every one of the 91 blur taps (visualizer.frag:19-33) adds the same offset to all fragments,
-// so for one tap k
+// so for one tap
 //     all fragments of a column share (ix, fx)     → the horizontal lerp is done once per column and row
 //     all fragments of a row    share (iy, fy)     → the vertical weights are warp-uniform table entries
-// One thread owns one fragment COLUMN and J consecutive fragment rows. Per tap it
-//   1. computes px, floor, fraction once                                   (4 FP + 3 INT)
-//   2. lerps 4 texel rows horizontally: H_r = T[r][ix] + fx*(T[r][ix+1]-T[r][ix])   (8 LDS + 12 FFMA;
-//      the window holds pre-differenced pair records, so one FFMA per channel)
-//   3. forms the vertical differences D_r = H_{r+1} - H_r                    (9 FADD)
-//   4. for each of its J rows adds  H_0 + sum_r D_r*clamp(py - r0 - r, 0, 1)  — the piecewise-linear
-//      interpolant through H_0..H_3 written with hinge functions, whose three weights come from a
-//      per-CTA shared table indexed (row group, tap, row): 1 broadcast LDS.128 + 9 FFMA per fragment;
-//      H_0 is common to the J rows and is accumulated once.
-// ≈ 15 instructions per (fragment, tap) against ≈ 40 for one-thread-per-fragment bilinear footprints
-// (visualizer_tiled.cuh), and a quarter of its shared-memory wavefronts. Mathematically identical to
-// the bilinear form; float32 re-association only (tests gate it against the literal transliteration).
+// One thread owns one fragment COLUMN and J consecutive fragment rows (a "row group"). A bilinear tap is
+// V(H) — the horizontal lerp H_r = T[r][ix] + fx*(T[r][ix+1]-T[r][ix]) of a few texel rows r (the window
+// holds pre-differenced pair records: one FFMA per channel), followed by a vertical interpolation whose
+// weights do not depend on the column. V is linear in H, which is what the kernel exploits:
+//   phase 1  the 21 taps with dx = 0 (rays 90°, 270° and the undisplaced tap) share ONE horizontal lerp
+//            per texel row; their vertical weights are summed per (row group, fragment row, texel row)
+//            into a table when the CTA starts: 21 taps cost one pass over <= 4*nq texel rows;
+//   phase 2  the 20 taps with dy = 0 (rays 0°, 180°; ray 0 counts twice, it also stands for the 9th
+//            direction of the float loop) sum their H first, V is applied once;
+//   phase 3  rays 45°/135° and 225°/315° pair up tap by tap (same dy): H is summed per pair, V once.
+// V over the 4 texel rows a row group can touch is written with hinge functions,
+//   V = H_0 + sum_r (H_{r+1}-H_r)*clamp(py - r0 - r, 0, 1),
+// whose three weights per (row group, tap group, fragment row) come from a per-CTA shared table: one
+// broadcast LDS.128 + 9 FFMA per fragment; H_0 is common to the J rows and is accumulated once.
+// 91 taps cost 60 horizontal gathers + 22 vertical applications per column: ≈ 4.4 k instructions and
+// ≈ 1.9 k shared-memory wavefronts per thread (8 fragments), against ≈ 26 k / 7.8 k for the
+// one-thread-per-pixel bilinear footprints of visualizer_tiled.cuh. Mathematically identical to the
+// literal loop; float32 re-association, and tap offsets that differ by < 1e-7 texel (sin 45° vs sin 135°
+// in float32, cos 90° = -4.4e-8) are treated as equal (tests gate it against the literal transliteration).
 //
 // CTA = 64 fragment columns x 4 row groups (256 threads), J = 8 or 4 rows per group chosen by the host
 // from the vertical texel step per fragment (4 texel rows must cover J fragment rows). The background
@@ -39,10 +46,17 @@ constexpr int VR_GROUPS = 4;           // row groups per CTA (threadIdx.y)
 constexpr int VR_THREADS = VR_COLS*VR_GROUPS;
 constexpr int VR_WIN_W = 64;           // window row stride, texels
 constexpr int VR_MAX_H = 40;           // window rows the launcher may ask for
-constexpr int VR_TAPS = 81;            // 10 (ray 0, weighted twice) + 70 (rays 1-7) + 1 (undisplaced)
 constexpr int VR_ROWS = 4;             // texel rows interpolated per tap: covers a vertical span < 2 texels
+constexpr int VR_HG = 21;              // vertical (hinge) groups: 0 = rays 0°/180°, 1-10 = rays 45°/135°, 11-20 = rays 225°/315°
+constexpr int VR_MAXQ = 6;             // phase 1 walks at most 4*VR_MAXQ texel rows
+constexpr int VR_VTAPS = 21;           // taps with dx = 0: rays 90°, 270°, the undisplaced tap
 
-struct RowsTaps { float dx[VR_TAPS + 3]; float dy[VR_TAPS + 3]; };
+struct RowsTaps {
+    float hdx[20];                     // phase 2: dx of ray 0 (10 walks), then ray 180°
+    float pdx[40];                     // phase 3: pair p = taps 2p, 2p+1 (rays 45°,135° for p < 10; rays 225°,315° after)
+    float gdy[VR_HG];                  // dy of each hinge group
+    float vdy[VR_VTAPS];               // phase 1: dy of rays 90°, 270°, then 0
+};
 __constant__ RowsTaps c_rows;
 
 struct VisRowsParams {
@@ -117,11 +131,13 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     extern __shared__ __align__(128) unsigned char vr_smem[];
     float4* rg = reinterpret_cast<float4*>(vr_smem);                                     // [win_h][64] (r, g, r'-r, g'-g)
     float2* bb = reinterpret_cast<float2*>(vr_smem + sizeof(float4)*VR_WIN_W*win_h);     // [win_h][64] (b, b'-b)
-    float4* tbl = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][81][J]
+    float4* tblH = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][VR_HG][J] hinge weights + row offset
+    float4* tblM = tblH + VR_GROUPS*VR_HG*J;                                             // [4][VR_MAXQ][J] merged weights of 4 texel rows
     __shared__ float red[2][VR_THREADS/32];
     __shared__ float cyS[VR_GROUPS][J];
     __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
     __shared__ int win[5];                                                               // x0, y0, fits, tma, table overflow
+    __shared__ unsigned int mhdr[VR_GROUPS][2];                                          // phase 1: first row offset, row quads
     __shared__ __align__(8) unsigned long long bar;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty*VR_COLS + tx;
@@ -184,13 +200,14 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         bulk_load_row(vr_smem + tid*(VR_WIN_W*4), src, VR_WIN_W*4, &bar);
     }
 
-    // ---- C. vertical table: hinge weights of every (row group, tap, row), warp-uniform in the main loop
+    // ---- C. vertical tables (warp-uniform in the main loop) ------------------------------------------
     if (window_ok) {
         const float y0f = float(y0);
         int bad = 0;
-        for (int e = tid; e < VR_GROUPS*VR_TAPS*J; e += VR_THREADS) {
-            const int g = e/(VR_TAPS*J), rem = e - g*(VR_TAPS*J), k = rem/J, r = rem - k*J;
-            const float dy = c_rows.dy[k];
+        // hinge weights of every (row group, tap group, fragment row)
+        for (int e = tid; e < VR_GROUPS*VR_HG*J; e += VR_THREADS) {
+            const int g = e/(VR_HG*J), rem = e - g*(VR_HG*J), k = rem/J, r = rem - k*J;
+            const float dy = c_rows.gdy[k];
             const float p0 = fmaf(dy, scale, cyS[g][0] - y0f), pl = fmaf(dy, scale, cyS[g][J - 1] - y0f);
             const float py = fmaf(dy, scale, cyS[g][r] - y0f);
             const float r0f = floorf(fminf(p0, pl));
@@ -200,7 +217,31 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             // byte offset of window row r0 in the (b, b'-b) plane, with the 2^23 exponent bits of the magic
             // floor of x folded in (modulo 2^32); the (r, g) plane uses twice this offset
             const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
-            tbl[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+            tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+        }
+        // merged weights of the dx = 0 taps: one thread per (row group, fragment row) owns its entries
+        if (tid < VR_GROUPS*J) {
+            const int g = tid/J, r = tid - g*J;
+            const float lo = fminf(cyS[g][0], cyS[g][J - 1]) - y0f, hi = fmaxf(cyS[g][0], cyS[g][J - 1]) - y0f;
+            const int ry0 = int(floorf(lo - scale*1.0001f));
+            const int ry1 = int(floorf(hi + scale*1.0001f)) + 1;                 // last texel row touched
+            const int nq = (ry1 - ry0 + 4) >> 2;
+            if (ry0 < 0 || nq < 1 || nq > VR_MAXQ || ry0 + 4*nq > win_h) {
+                bad = 1;
+            } else {
+                float* mine = reinterpret_cast<float*>(tblM + (g*VR_MAXQ)*J + r);  // quad q at mine[q*J*4 .. +3]
+                for (int q = 0; q < VR_MAXQ; q++) tblM[(g*VR_MAXQ + q)*J + r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float cy = cyS[g][r] - y0f;
+                for (int k = 0; k < VR_VTAPS; k++) {
+                    const float py = fmaf(c_rows.vdy[k], scale, cy);
+                    const float rf = floorf(py), f = py - rf;
+                    const int lo_i = int(rf) - ry0, hi_i = lo_i + 1;
+                    if (lo_i < 0 || hi_i >= 4*nq) { bad = 1; continue; }
+                    mine[(lo_i >> 2)*(J*4) + (lo_i & 3)] += 1.0f - f;
+                    mine[(hi_i >> 2)*(J*4) + (hi_i & 3)] += f;
+                }
+                if (r == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
+            }
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
     }
@@ -245,7 +286,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     __syncthreads();
     const bool fits = window_ok && win[4] == 0;
 
-    // ---- D. blur: taps x rows -----------------------------------------------------------------------
+    // ---- D. blur ------------------------------------------------------------------------------------
     float base0 = 0.0f, base1 = 0.0f, base2 = 0.0f;
     float acc[J][3];
     #pragma unroll
@@ -254,24 +295,27 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         const float cx = tapx - float(x0);                         // tile-local, >= 1 by construction of x0
         const char* rgB = reinterpret_cast<const char*>(rg);
         const char* bbB = reinterpret_cast<const char*>(bb);
-        const float4* T = tbl + ty*(VR_TAPS*J);
-        auto tap = [&](int k) {
-            const float4 e0 = T[k*J];
-            const float px = fmaf(c_rows.dx[k], scale, cx);
+        // Horizontal lerp of the 4 texel rows starting at byte offset `rowoff` (b plane units), at column
+        // position cx + dx*scale: H[r] (+)= T + a*(T' - T)
+        auto gather = [&](float dx, unsigned int rowoff, float (&H)[VR_ROWS][3], const bool first) {
+            const float px = fmaf(dx, scale, cx);
             // floor for 0.5 <= p < 2^22: p + (2^23 - 0.5) rounds to floor(p) + 2^23 (ties land on either
             // neighbour; the interpolant is continuous there)
             const float tx_ = px + 8388607.5f;
             const float a = px - (tx_ - 8388608.0f);
-            const unsigned int off8 = __float_as_uint(e0.w) + (__float_as_uint(tx_) << 3);
+            const unsigned int off8 = rowoff + (__float_as_uint(tx_) << 3);
             const char* pr = rgB + 2u*off8;
             const char* pb = bbB + off8;
-            float H[VR_ROWS][3];
             #pragma unroll
             for (int r = 0; r < VR_ROWS; r++) {
                 const float4 q = *reinterpret_cast<const float4*>(pr + r*(VR_WIN_W*16));
                 const float2 s = *reinterpret_cast<const float2*>(pb + r*(VR_WIN_W*8));
-                H[r][0] = fmaf(a, q.z, q.x); H[r][1] = fmaf(a, q.w, q.y); H[r][2] = fmaf(a, s.y, s.x);
+                if (first) { H[r][0] = fmaf(a, q.z, q.x); H[r][1] = fmaf(a, q.w, q.y); H[r][2] = fmaf(a, s.y, s.x); }
+                else { H[r][0] = fmaf(a, q.z, H[r][0] + q.x); H[r][1] = fmaf(a, q.w, H[r][1] + q.y); H[r][2] = fmaf(a, s.y, H[r][2] + s.x); }
             }
+        };
+        // Vertical interpolation of H for the J fragment rows with the hinge weights T[0..J)
+        auto apply = [&](const float4* T, const float4 e0, const float (&H)[VR_ROWS][3]) {
             base0 += H[0][0]; base1 += H[0][1]; base2 += H[0][2];
             float D[VR_ROWS - 1][3];
             #pragma unroll
@@ -280,20 +324,57 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             }
             #pragma unroll
             for (int r = 0; r < J; r++) {
-                const float4 e = (r == 0) ? e0 : T[k*J + r];
+                const float4 e = (r == 0) ? e0 : T[r];
                 #pragma unroll
                 for (int c = 0; c < 3; c++)
                     acc[r][c] = fmaf(e.x, D[0][c], fmaf(e.y, D[1][c], fmaf(e.z, D[2][c], acc[r][c])));
             }
         };
-        // ray 0 (angle 0) stands for itself and for the 9th float-loop direction (visualizer_tiled.cuh): weight 2
+
+        // phase 1: the dx = 0 taps through the merged weights, 4 texel rows at a time
+        {
+            const float4* M = tblM + ty*(VR_MAXQ*J);
+            unsigned int rowoff = mhdr[ty][0];
+            const int nq = int(mhdr[ty][1]);
+            #pragma unroll 1
+            for (int q = 0; q < nq; q++, rowoff += 4u*(VR_WIN_W*8u)) {
+                float H[VR_ROWS][3];
+                gather(0.0f, rowoff, H, true);
+                #pragma unroll
+                for (int r = 0; r < J; r++) {
+                    const float4 w = M[q*J + r];
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        acc[r][c] = fmaf(w.x, H[0][c], fmaf(w.y, H[1][c], fmaf(w.z, H[2][c], fmaf(w.w, H[3][c], acc[r][c]))));
+                }
+            }
+        }
+        const float4* T = tblH + ty*(VR_HG*J);
+        // phase 2: the dy = 0 taps; ray 0 is weighted twice
+        {
+            const float4 e0 = T[0];
+            const unsigned int rowoff = __float_as_uint(e0.w);
+            float H[VR_ROWS][3];
+            gather(c_rows.hdx[0], rowoff, H, true);
+            #pragma unroll 3
+            for (int t = 1; t < 10; t++) gather(c_rows.hdx[t], rowoff, H, false);
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS; r++) { H[r][0] += H[r][0]; H[r][1] += H[r][1]; H[r][2] += H[r][2]; }
+            #pragma unroll 2
+            for (int t = 10; t < 20; t++) gather(c_rows.hdx[t], rowoff, H, false);
+            apply(T, e0, H);
+        }
+        // phase 3: the diagonal rays, two taps per vertical group
         #pragma unroll 2
-        for (int k = 0; k < 10; k++) tap(k);
-        base0 += base0; base1 += base1; base2 += base2;
-        #pragma unroll
-        for (int r = 0; r < J; r++) { acc[r][0] += acc[r][0]; acc[r][1] += acc[r][1]; acc[r][2] += acc[r][2]; }
-        #pragma unroll 2
-        for (int k = 10; k < VR_TAPS; k++) tap(k);
+        for (int p = 0; p < 20; p++) {
+            const float4* Tp = T + (p + 1)*J;
+            const float4 e0 = Tp[0];
+            const unsigned int rowoff = __float_as_uint(e0.w);
+            float H[VR_ROWS][3];
+            gather(c_rows.pdx[2*p], rowoff, H, true);
+            gather(c_rows.pdx[2*p + 1], rowoff, H, false);
+            apply(Tp, e0, H);
+        }
     }
 
     // ---- E. rest of main() per fragment, 8-bit store rule per sub-sample, box sum --------------------
@@ -399,8 +480,21 @@ static int build_rows_tables() {
     }
     if (n != 90) SFB_FAIL(SFB_ESTATE, "blur table has %d taps, expected 90", n);
     blur.tap[90] = make_float2(0.0f, 0.0f); blur.tap[91] = make_float2(0.0f, 0.0f);
-    for (int k = 0; k < 80; k++) { rows.dx[k] = blur.tap[k].x; rows.dy[k] = blur.tap[k].y; }
-    rows.dx[80] = 0.0f; rows.dy[80] = 0.0f;
+    // ray r, walk t = blur.tap[10*r + t]; rays at 0°, 45°, ..., 315° (the 9th, at 360°, is folded into ray 0)
+    auto ray = [&](int r, int t) { return blur.tap[10*r + t]; };
+    const float tol = 1.0e-6f;
+    for (int t = 0; t < 10; t++) {
+        rows.hdx[t] = ray(0, t).x; rows.hdx[10 + t] = ray(4, t).x;
+        rows.pdx[2*t] = ray(1, t).x; rows.pdx[2*t + 1] = ray(3, t).x;  rows.gdy[1 + t] = ray(1, t).y;
+        rows.pdx[20 + 2*t] = ray(5, t).x; rows.pdx[20 + 2*t + 1] = ray(7, t).x; rows.gdy[11 + t] = ray(5, t).y;
+        rows.vdy[t] = ray(2, t).y; rows.vdy[10 + t] = ray(6, t).y;
+        // the groupings rest on these coincidences of the float32 table
+        if (fabsf(ray(0, t).y) > tol || fabsf(ray(4, t).y) > tol || fabsf(ray(2, t).x) > tol || fabsf(ray(6, t).x) > tol
+            || fabsf(ray(1, t).y - ray(3, t).y) > tol || fabsf(ray(5, t).y - ray(7, t).y) > tol
+            || fabsf(ray(8, t).x - ray(0, t).x) > tol || fabsf(ray(8, t).y - ray(0, t).y) > tol)
+            SFB_FAIL(SFB_ESTATE, "blur table symmetry broken at walk %d", t);
+    }
+    rows.gdy[0] = 0.0f; rows.vdy[20] = 0.0f;
     SFB_CUDA(cudaMemcpyToSymbol(c_blur, &blur, sizeof(blur)));
     SFB_CUDA(cudaMemcpyToSymbol(c_rows, &rows, sizeof(rows)));
     if (device < 64) done[device] = true;
@@ -409,14 +503,16 @@ static int build_rows_tables() {
 
 template <int S, int J> static cudaError_t launch_rows(const VisRowsParams& VP, cudaStream_t st) {
     static bool configured = false;
-    const size_t table = sizeof(float4)*VR_GROUPS*VR_TAPS*J;
+    const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
+    const size_t epilogue = sizeof(float4)*J*VR_THREADS + size_t(VR_GROUPS*J)*VR_COLS*3;   // stash + rgb24 staging
     if (!configured) {
         const size_t most = (sizeof(float4) + sizeof(float2))*VR_WIN_W*VR_MAX_H + table;
         cudaError_t e = cudaFuncSetAttribute(visualizer_rows_kernel<S, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
+    size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
+    if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
     visualizer_rows_kernel<S, J><<<grid, block, smem, st>>>(VP);
     return cudaSuccess;
@@ -454,7 +550,7 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, bool*
     else return SFB_OK;
     const double reach = double(scale)*1.0001 + 1.0;
     if ((VR_COLS - 1)*sx + 2.0*reach + 9.0 > double(VR_WIN_W - 1)) return SFB_OK;
-    const int win_h = int(ceil((VR_GROUPS*J - 1)*sy + 2.0*reach)) + 7;
+    const int win_h = int(ceil((VR_GROUPS*J - 1)*sy + 2.0*reach)) + 11;   // + alignment, neighbours, the last row quad
     if (win_h > VR_MAX_H) return SFB_OK;
     if (int e = build_rows_tables()) return e;
     VisRowsParams VP;
