@@ -351,9 +351,9 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && ssaa <= 4) {
         // production path of the headline scene: the separable kernel when the camera allows it, ...
         if (!(flags & SFB_RENDER_TILED)) {
-            bool launched = false;
+            int launched = 0;
             if (int e = sfb_visualizer_rows_launch(P, ctx->stream, &launched)) return e;
-            if (launched) { SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
+            if (launched) { ctx->launches += launched - 1; SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
         }
         // ... else one thread per output pixel over a shared-memory window of the background
         VisualizerParams VP;

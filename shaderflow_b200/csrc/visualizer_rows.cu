@@ -62,6 +62,7 @@ __constant__ RowsTaps c_rows;
 struct VisRowsParams {
     RenderParams R;
     int win_h;                         // window rows staged (dynamic shared memory is sized for it)
+    int slot;                          // g_frame entry written by visualizer_frame_consts_kernel for this frame
     int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
 };
 
@@ -70,46 +71,72 @@ SFB_DEV void bulk_load_row(void* dst, const void* src, unsigned int bytes, unsig
         :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// pow(x, y) for x >= 0 through exp2f(y*log2f(x)) (libdevice, <= 2 ulp each): the exponents used here are
-// <= 0.5 in magnitude, which shrinks the relative error of log2f; pow(0, y > 0) = 0 like powf
-SFB_DEV float pow_pos(float x, float y) { return exp2f(y*log2f(x)); }
+// MUFU-direct square root / log2 / exp2 (PTX .approx: relative error <= 2^-22, against <= 2 ulp for the
+// libdevice functions the literal transliteration calls — 3 to 6 times fewer instructions, no slow-path
+// branches). The back end is evaluated once per fragment and feeds an 8-bit store: 1e-6 is invisible.
+SFB_DEV float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SFB_DEV float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SFB_DEV float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// pow(x, y) for x >= 0 and the small |y| used here (<= 0.5, which shrinks the error of lg2); pow(0, y > 0) = 0
+SFB_DEV float pow_pos(float x, float y) { return fast_ex2(y*fast_lg2(x)); }
 
-// Per-frame constants of visualizer.frag:35-73 (functions of the uniforms only)
-struct BackConsts { float std5, mscale, vexp; };
+// Per-frame constants of visualizer.frag (functions of the uniforms only), evaluated once per frame by
+// visualizer_frame_consts_kernel with the same libdevice calls as the literal transliteration
+struct FrameConsts {
+    float zf, wobx, woby, scale;       // background zoom factor, wobble, blur radius in texels (:16-17,21)
+    float std5, mscale, vexp, pad;     // 5*iAudioSTD, 1 - 0.4*pow(|vol|, 0.5), 0.1 + 0.15*vol (:35,39,71)
+};
+constexpr int VR_SLOTS = 64;
+__device__ FrameConsts g_frame[VR_SLOTS];
+
+__global__ void visualizer_frame_consts_kernel(float iTime, float volume, float stddev, float fh, int slot) {
+    if (threadIdx.x != 0) return;
+    FrameConsts F;
+    F.zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*volume - 0.03f;
+    F.wobx = 0.005f*cosf(iTime*3.25135f); F.woby = 0.005f*sinf(iTime*1.153469f);
+    F.scale = (0.01f*clamp(powf(volume, 2.5f), 0.0f, 0.3f))*fh;     // st displacement → texels (hw*fw == fh)
+    F.std5 = 5.0f*stddev;
+    F.mscale = 1.0f - 0.4f*powf(fabsf(volume), 0.5f);
+    F.vexp = 0.1f + 0.15f*volume;
+    F.pad = 0.0f;
+    g_frame[slot] = F;
+}
+
+// What the back end reads of iSpectrogram when it is the usual RG32F column (spectrogram.py:272-282)
+struct SpecColumn { const float2* texels; int h, ry; };
 
 // Everything of main() after the blur loop (visualizer.frag:35-73) for the separable camera: the column
 // gives (agluv.x, astuv.x, uv.x, waveform thresholds), the row gives (agluv.y, astuv.y, uv.y). Same
-// mathematics and operation order as vis_back (visualizer_tiled.cuh); pow with a constant exponent 6 is
-// three multiplies, the fractional powers go through pow_pos, divisions by constants are multiplications.
-SFB_DEV vec3 vis_back_sep(const RenderParams& P, const BackConsts& K, vec3 rgb, float agx, float asx, float uvx,
-                          float wavx, float wavy, float agy, float asy, float uvy) {
+// mathematics and operation order as vis_back (visualizer_tiled.cuh), written branch-free so that two
+// fragments interleave: pow with the constant exponent 6 is three multiplies, the fractional powers go
+// through pow_pos, divisions by constants are multiplications, square roots are MUFU-direct.
+SFB_DEV vec3 vis_back_sep(const RenderParams& P, const FrameConsts& K, const SpecColumn& sc, vec3 rgb, float agx, float asx,
+                          float uvx, float wavx, float wavy, float agy, float asy, float uvy) {
     const vec3 space = mk3(1.0f, 11.0f, 26.0f)/255.0f;
-    const float t = clamp(sqrtf(agx*agx + agy*agy) - 0.3f, 0.0f, 1.0f), t2 = t*t;
+    const float t = clamp(fast_sqrt(agx*agx + agy*agy) - 0.3f, 0.0f, 1.0f), t2 = t*t;
     rgb = rgb*(1.0f + K.std5*(t2*t2*t2));
     const float c = -4.37113883e-08f, sn = -1.0f;                 // cos, sin of float32(-PI/2)
     const float mx = (c*uvx + sn*uvy)*K.mscale, my = ((-sn)*uvx + c*uvy)*K.mscale;
     const float radius = 0.17f;
     const float circle = fabsf(atan2f(my, mx)*(1.0f/PI));
-    // texture(iSpectrogram, (0, circle)): NEAREST on an RG32F column (spectrogram.py:272-282)
-    const DevSampler& sp = P.tex[1];
-    float2 sv;
-    if (sp.dtype == SFB_DTYPE_F32 && sp.padded == 2 && sp.w == 1 && sp.filter == SFB_FILTER_NEAREST) {
-        sv = __ldg(reinterpret_cast<const float2*>(sp.lin) + wrap_index(int(floorf(circle*float(sp.h))), sp.h, sp.ry));
+    float2 sv;                                                    // texture(iSpectrogram, (0, circle)), NEAREST
+    if (sc.texels) {
+        sv = __ldg(sc.texels + wrap_index(int(floorf(circle*float(sc.h))), sc.h, sc.ry));
     } else {
-        const vec4 q = texture<false>(sp, mk2(0.0f, circle)); sv = make_float2(q.x, q.y);
+        const vec4 q = texture<false>(P.tex[1], mk2(0.0f, circle)); sv = make_float2(q.x, q.y);
     }
     const float h = clamp(circle*0.5f, 0.0f, 1.0f);
     const float fscale = 0.05f + 3.0f*(h*h*(3.0f - 2.0f*h));
-    const float lm = sqrtf(mx*mx + my*my);
-    if (lm < radius) {
-        rgb = rgb*0.5f;
-    } else {
-        const float bar = sqrtf(((my < 0.0f) ? sv.x : sv.y)*0.001f)*fscale;
-        const float r = radius + 0.5f*bar;
-        if (lm < r) { const float g = clamp(0.5f + bar, 0.0f, 1.0f); rgb = mix(rgb, mk3(1.0f), g*g*(3.0f - 2.0f*g)); }
-        else        rgb = rgb*pow_pos((lm - r)*0.5f, 0.05f);
-    }
-    { const float g = clamp(sqrtf(uvx*uvx + uvy*uvy)*0.05f, 0.0f, 1.0f); rgb = mix(rgb, space, g*g*(3.0f - 2.0f*g)); }
+    const float lm = fast_sqrt(mx*mx + my*my);
+    const float bar = fast_sqrt(((my < 0.0f) ? sv.x : sv.y)*0.001f)*fscale;
+    const float r = radius + 0.5f*bar;
+    // inside the disc: rgb/2; on the bar: mix(rgb, 1, smoothstep(0.5 + bar)); outside: rgb*pow(.., 0.05)
+    const float g = clamp(0.5f + bar, 0.0f, 1.0f), sm = g*g*(3.0f - 2.0f*g);
+    const float dim = pow_pos((lm - r)*0.5f, 0.05f);
+    const bool inside = lm < radius, ring = lm < r;
+    const float mul = inside ? 0.5f : (ring ? (1.0f - sm) : dim), add = (!inside && ring) ? sm : 0.0f;
+    rgb = rgb*mul + add;
+    { const float e = clamp(fast_sqrt(uvx*uvx + uvy*uvy)*0.05f, 0.0f, 1.0f); rgb = mix(rgb, space, e*e*(3.0f - 2.0f*e)); }
     rgb = rgb*pow_pos((asx*(1.0f - asy))*(asy*(1.0f - asx))*20.0f, K.vexp);
     if (1.0f - agy < wavx) rgb = rgb*0.8f;
     if (1.0f + agy < wavy) rgb = rgb*0.8f;
@@ -123,7 +150,10 @@ __device__ __noinline__ void visualizer_unfitted(const RenderParams& P, int i, i
 }
 
 template <int S, int J>
-__global__ void __launch_bounds__(VR_THREADS, 2)
+#ifndef VR_MIN_CTAS
+#define VR_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(VR_THREADS, VR_MIN_CTAS)
 visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     static_assert(J % S == 0 && VR_COLS % S == 0, "a CTA shades whole output pixels");
     const RenderParams& P = VP.R;
@@ -145,11 +175,9 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     const int jb = blockIdx.y*(VR_GROUPS*J) + ty*J;               // first fragment row of this thread
     const DevSampler& bg = P.tex[0];
     const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
-    const float iTime = P.u.iTime, iAudioVolume = P.u.extra[0][0];
-    const float zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*iAudioVolume - 0.03f;
-    const vec2 wobble = 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
-    const float intensity = 0.01f*clamp(powf(iAudioVolume, 2.5f), 0.0f, 0.3f);
-    const float scale = intensity*fh;                             // st displacement → texels (hw*fw == fh)
+    const FrameConsts K = g_frame[VP.slot];
+    const float zf = K.zf, scale = K.scale;
+    const vec2 wobble = mk2(K.wobx, K.woby);
 
     // ---- A. centre-tap positions: x per column, y per row (coordinates clamped onto the target) ----
     const int ic = min(i, P.Wr - 1), jc = min(jb, P.Hr - 1);
@@ -173,8 +201,10 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     if (tid == 0) {
         float ax = red[0][0], bx = red[1][0], ay = cyS[0][0], by = cyS[0][0];
         for (int w = 1; w < VR_THREADS/32; w++) { ax = fminf(ax, red[0][w]); bx = fmaxf(bx, red[1][w]); }
-        for (int g = 0; g < VR_GROUPS; g++)
-            for (int r = 0; r < J; r++) { ay = fminf(ay, cyS[g][r]); by = fmaxf(by, cyS[g][r]); }
+        {   // rows are affine in j: the extremes are the first and the last row of the tile
+            const float first = cyS[0][0], last = cyS[VR_GROUPS - 1][J - 1];
+            ay = fminf(first, last); by = fmaxf(first, last);
+        }
         const float reach = scale*1.0001f + 1.0f;                 // |dir*walk| <= 1.0000001; +1 keeps local coords >= 1
         // bulk copies need 16-byte aligned rows: x0 % 4 == 0
         const int x0 = (int(floorf(ax - reach)) - 1) & ~3, y0 = int(floorf(ay - reach)) - 1;
@@ -219,29 +249,21 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
             tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
         }
-        // merged weights of the dx = 0 taps: one thread per (row group, fragment row) owns its entries
-        if (tid < VR_GROUPS*J) {
-            const int g = tid/J, r = tid - g*J;
+        // merged weights of the dx = 0 taps: W[g][row][r] = sum over the 21 taps of hat(py - row), the
+        // bilinear weight of texel row `row` (hat(t) = max(0, 1 - |t|)); one entry per loop trip
+        for (int e = tid; e < VR_GROUPS*VR_MAXQ*4*J; e += VR_THREADS) {
+            const int g = e/(VR_MAXQ*4*J), rem = e - g*(VR_MAXQ*4*J), row = rem/J, r = rem - row*J;
             const float lo = fminf(cyS[g][0], cyS[g][J - 1]) - y0f, hi = fmaxf(cyS[g][0], cyS[g][J - 1]) - y0f;
             const int ry0 = int(floorf(lo - scale*1.0001f));
             const int ry1 = int(floorf(hi + scale*1.0001f)) + 1;                 // last texel row touched
             const int nq = (ry1 - ry0 + 4) >> 2;
-            if (ry0 < 0 || nq < 1 || nq > VR_MAXQ || ry0 + 4*nq > win_h) {
-                bad = 1;
-            } else {
-                float* mine = reinterpret_cast<float*>(tblM + (g*VR_MAXQ)*J + r);  // quad q at mine[q*J*4 .. +3]
-                for (int q = 0; q < VR_MAXQ; q++) tblM[(g*VR_MAXQ + q)*J + r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                const float cy = cyS[g][r] - y0f;
-                for (int k = 0; k < VR_VTAPS; k++) {
-                    const float py = fmaf(c_rows.vdy[k], scale, cy);
-                    const float rf = floorf(py), f = py - rf;
-                    const int lo_i = int(rf) - ry0, hi_i = lo_i + 1;
-                    if (lo_i < 0 || hi_i >= 4*nq) { bad = 1; continue; }
-                    mine[(lo_i >> 2)*(J*4) + (lo_i & 3)] += 1.0f - f;
-                    mine[(hi_i >> 2)*(J*4) + (hi_i & 3)] += f;
-                }
-                if (r == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
-            }
+            if (ry0 < 0 || nq < 1 || nq > VR_MAXQ || ry0 + 4*nq > win_h) { bad = 1; continue; }
+            const float cy = cyS[g][r] - y0f - float(ry0 + row);
+            float w = 0.0f;
+            #pragma unroll 7
+            for (int k = 0; k < VR_VTAPS; k++) w += fmaxf(1.0f - fabsf(fmaf(c_rows.vdy[k], scale, cy)), 0.0f);
+            reinterpret_cast<float*>(tblM + (g*VR_MAXQ + (row >> 2))*J + r)[row & 3] = w;
+            if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
     }
@@ -393,17 +415,20 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     constexpr int RB = PX*3;                                       // staged bytes per output row
     const bool col_in = i < P.Wr;
     const bool words = (P.comps == 3) && (P.W % 4 == 0) && (int(blockIdx.x)*PX + PX <= P.W);
-    BackConsts K;
-    K.std5 = 5.0f*P.u.extra[1][0];
-    K.mscale = 1.0f - 0.4f*powf(fabsf(iAudioVolume), 0.5f);
-    K.vexp = 0.1f + 0.15f*iAudioVolume;
+    SpecColumn sc;
+    {
+        const DevSampler& sp = P.tex[1];
+        const bool column = sp.dtype == SFB_DTYPE_F32 && sp.padded == 2 && sp.w == 1 && sp.filter == SFB_FILTER_NEAREST;
+        sc.texels = column ? reinterpret_cast<const float2*>(sp.lin) : nullptr; sc.h = sp.h; sc.ry = sp.ry;
+    }
     const float agx = vc.f.agluv.x, asx = vc.f.astuv.x, uvx = vc.uv.x;
     float wavx, wavy;
     { const vec4 w = texture<false>(P.tex[2], mk2(asx, 0.0f)); wavx = 0.2f*w.x; wavy = 0.2f*w.y; }
-    #pragma unroll 1
+    // two fragments in flight per iteration (the back end is a long dependent chain)
+    #pragma unroll (S == 1 ? 2 : 1)
     for (int pr = 0; pr < J/S; pr++) {
         unsigned int r8 = 0, g8 = 0, b8 = 0;
-        #pragma unroll 1
+        #pragma unroll (S >= 2 ? 2 : 1)
         for (int s = 0; s < S; s++) {
             const int r = pr*S + s;
             vec3 c;
@@ -415,7 +440,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
                 const float4 q = stash[r*VR_THREADS + tid];
                 const float4 row = rowS[ty][r];
                 c = (VP.debug & 2) ? mk3(q.x, q.y, q.z)
-                                   : vis_back_sep(P, K, mk3(q.x, q.y, q.z), agx, asx, uvx, wavx, wavy, row.x, row.y, row.z);
+                                   : vis_back_sep(P, K, sc, mk3(q.x, q.y, q.z), agx, asx, uvx, wavx, wavy, row.x, row.y, row.z);
             }
             r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
             g8 += (unsigned int)__float2int_rn(__saturatef(c.y)*255.0f);
@@ -501,7 +526,7 @@ static int build_rows_tables() {
     return SFB_OK;
 }
 
-template <int S, int J> static cudaError_t launch_rows(const VisRowsParams& VP, cudaStream_t st) {
+template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
     static bool configured = false;
     const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
     const size_t epilogue = sizeof(float4)*J*VR_THREADS + size_t(VR_GROUPS*J)*VR_COLS*3;   // stash + rgb24 staging
@@ -514,13 +539,18 @@ template <int S, int J> static cudaError_t launch_rows(const VisRowsParams& VP, 
     size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
     if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
+    // frame constants first (same stream): consecutive frames rotate through the slots
+    static unsigned int next_slot = 0;
+    VP.slot = int(next_slot++ % VR_SLOTS);
+    const sfb_uniforms& u = VP.R.u;
+    visualizer_frame_consts_kernel<<<1, 32, 0, st>>>(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h), VP.slot);
     visualizer_rows_kernel<S, J><<<grid, block, smem, st>>>(VP);
     return cudaSuccess;
 }
 
 // Launch planning on the host: the same vis_front the kernel evaluates gives the texel step per fragment.
-int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, bool* launched) {
-    *launched = false;
+int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched) {
+    *launched = 0;
     static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
     if (disabled) return SFB_OK;
     const sfb_uniforms& u = P.u;
@@ -564,6 +594,6 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, bool*
         if (S == 1) e = launch_rows<1, 4>(VP, stream); else if (S == 2) e = launch_rows<2, 4>(VP, stream); else e = launch_rows<4, 4>(VP, stream);
     }
     SFB_CUDA(e);
-    *launched = true;
+    *launched = 2;                                                 // frame constants + the frame
     return SFB_OK;
 }

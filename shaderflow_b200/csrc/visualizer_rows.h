@@ -4,6 +4,6 @@
 #include "scenes.cuh"
 
 // Plans and launches the separable kernel when the frame qualifies (axis-aligned 2D camera, ssaa 1/2/4,
-// vertical texel step small enough, window fits); *launched says whether it did. P must be fully filled
+// vertical texel step small enough, window fits); *launched = kernels launched (0 when it did not). P must be fully filled
 // (fill_params + geometry) with P.fast set.
-int sfb_visualizer_rows_launch(const glsl::RenderParams& P, cudaStream_t stream, bool* launched);
+int sfb_visualizer_rows_launch(const glsl::RenderParams& P, cudaStream_t stream, int* launched);
