@@ -29,6 +29,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+RESULT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np  # noqa: E402
 
@@ -157,7 +160,7 @@ def run_reference(args, rank: int) -> None:
                 config=dict(workload=WORKLOAD, step="bounded sample of one frame: row bands shaded on every host core, extrapolated"),
                 cpu_baseline=dict(value=value, unit="frames/s", cores=last["cores"], kind="port", sample=last["sample"]),
                 e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT, flush=True)
 
 
 # -------------------------------------------------------------------------------------------------- #
@@ -320,7 +323,7 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
                 gpu_launches=int(launches), roofline=roofline, stft=stft)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args)
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT, flush=True)
 
 
 def main():

@@ -44,6 +44,9 @@ def init_process_group(backend: Optional[str] = None) -> tuple[int, int]:
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # the frame exchange overlaps with shading: keep NCCL's point-to-point kernels small (every
+            # resident NCCL CTA displaces shading CTAs on its SM)
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "8")
             torch.cuda.set_device(local)
             dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:
@@ -60,9 +63,99 @@ class FrameGather:
     `local_frames` is this rank's [n_local, ...] uint8 tensor (frames of its shard, in order). Blocks
     of at most `chunk` frames travel per message so rank 0 needs only `chunk` frames of staging."""
 
-    def __init__(self, n_frames: int, rank: int, world: int, chunk: int = 32, group=None):
+    def __init__(self, n_frames: int, rank: int, world: int, chunk: int = 32, group=None, ahead: int = 8):
         self.n_frames, self.rank, self.world, self.chunk, self.group = n_frames, rank, world, max(1, chunk), group
+        self.ahead = max(1, ahead)
+        self._works: list = []          # sender: (work, block) pairs in flight
+        self._plan: list = []           # root: (peer, frames) of every remote block, in time order
+        self._slots: list = []          # root: ring of receive buffers
+        self._posted: list = []         # root: (work, slot, frames) of the irecvs in flight, in time order
+        self._next = 0                  # root: next plan entry to post
+        self._full = None               # root: {peer: [frames, ...]} when every remote frame is staged
+        self._rounds: list = []         # root: works of each batched round of receives
 
+    # -- overlapped form: the exchange runs while the ranks are still shading ----------------------------
+    # sender:  send_block(frames) as soon as a block of its shard is complete, finish() at the end
+    # root:    post(shape, dtype, device) before shading, then `for block in drain()` after its own frames
+    def send_block(self, frames: torch.Tensor) -> None:
+        """Non-blocking send of a finished block of this rank's shard (in order) to rank 0"""
+        import torch.distributed as dist
+        assert self.rank != 0
+        for a in range(0, frames.shape[0], self.chunk):
+            block = frames[a:a + self.chunk].contiguous()
+            self._works.append((dist.isend(block, dst=0, group=self.group), block))
+
+    def finish(self) -> None:
+        for work, _ in self._works:
+            work.wait()
+        self._works.clear()
+
+    def post(self, frame_shape, dtype, device, budget_bytes: Optional[int] = None) -> None:
+        """Root: posts the receives before this rank starts shading, so remote frames arrive over NVLink
+        while every rank is still busy.
+
+        When all remote frames fit `budget_bytes` of staging (default 24 GiB, SFB_GATHER_BUDGET_GB) the
+        receives are posted round by round — block b of EVERY peer in one batched group, the order in which
+        the senders finish them — and only the consumption is in time order. Larger exports fall back to a
+        ring of `ahead` blocks received strictly in time order (the later peers then wait for their turn)."""
+        import torch.distributed as dist
+        assert self.rank == 0
+        if budget_bytes is None:
+            budget_bytes = int(float(os.environ.get("SFB_GATHER_BUDGET_GB", "24"))*(1 << 30))
+        self._plan, self._rounds, self._full = [], [], None
+        shards = {peer: shard_range(self.n_frames, peer, self.world) for peer in range(1, self.world)}
+        for peer, (p0, p1) in shards.items():
+            self._plan += [(peer, min(self.chunk, p1 - p0 - a)) for a in range(0, p1 - p0, self.chunk)]
+        frame_bytes = torch.empty((), dtype=dtype).element_size()
+        for d in frame_shape:
+            frame_bytes *= int(d)
+        remote = sum(p1 - p0 for p0, p1 in shards.values())
+        if remote*frame_bytes <= budget_bytes:
+            self._full = {peer: torch.empty((p1 - p0, *frame_shape), dtype=dtype, device=device) for peer, (p0, p1) in shards.items()}
+            most = max((p1 - p0 for p0, p1 in shards.values()), default=0)
+            for a in range(0, most, self.chunk):
+                ops = [dist.P2POp(dist.irecv, buf[a:a + self.chunk], peer, self.group)
+                       for peer, buf in self._full.items() if a < buf.shape[0]]
+                self._rounds.append(dist.batch_isend_irecv(ops) if ops else [])
+            return
+        n = min(self.ahead, len(self._plan))
+        self._slots = [torch.empty((self.chunk, *frame_shape), dtype=dtype, device=device) for _ in range(n)]
+        self._posted, self._next = [], 0
+        for slot in range(n):
+            self._post_next(slot)
+
+    def _post_next(self, slot: int) -> None:
+        import torch.distributed as dist
+        if self._next >= len(self._plan):
+            return
+        peer, frames = self._plan[self._next]
+        self._next += 1
+        block = self._slots[slot][:frames]
+        self._posted.append((dist.irecv(block, src=peer, group=self.group), slot, frames))
+
+    def drain(self) -> Iterator[torch.Tensor]:
+        """Root: yields every remote block in time order. In ring mode the block's memory is reused for a
+        later receive once the consumer has enqueued its use of it and asks for the next block."""
+        assert self.rank == 0
+        if self._full is not None:
+            waited = 0
+            for peer, buf in self._full.items():
+                for b, a in enumerate(range(0, buf.shape[0], self.chunk)):
+                    while waited <= b:                       # round b carries block b of every peer
+                        for work in self._rounds[waited]:
+                            work.wait()
+                        waited += 1
+                    yield buf[a:a + self.chunk]
+            self._full, self._rounds = None, []
+            return
+        while self._posted:
+            work, slot, frames = self._posted.pop(0)
+            work.wait()
+            yield self._slots[slot][:frames]
+            self._post_next(slot)
+        self._slots = []
+
+    # -- plain form: everything after the fact (kept for small jobs and the host tests) ------------------
     def stream(self, local_frames: torch.Tensor) -> Iterator[torch.Tensor]:
         import torch.distributed as dist
         start, stop = shard_range(self.n_frames, self.rank, self.world)

@@ -354,11 +354,18 @@ class ShaderScene(ShaderModule):
         if rank == 0:
             export.open_bar()
         first, last = frames if frames is not None else (0, export.total_frames)
-        staging = None
+        staging, gather, sent = None, None, 0
         if sharded:
+            # Rank 0 treats its own range like a single-GPU export (frames go straight to the sink ring) and
+            # has the receives of the other ranks' blocks posted before it starts shading; the other ranks
+            # shade into HBM and send each finished block without waiting (distributed.FrameGather).
             import torch
             first, last = D.shard_range(export.total_frames, rank, world)
-            staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
+            gather = D.FrameGather(export.total_frames, rank, world, chunk=4)
+            if rank == 0:
+                gather.post((self.height, self.width, 3), torch.uint8, f"cuda:{self.device}")
+            else:
+                staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
 
         def prepare(index: int) -> None:
             """Decides, before frame `index` is stepped, whether it is shaded and where to"""
@@ -376,7 +383,10 @@ class ShaderScene(ShaderModule):
                 continue
             if self.render_enabled:
                 if staging is not None:
-                    pass                                      # stays in HBM until the reassembly below
+                    done = export.frame - first + 1            # frames of the shard shaded so far
+                    if done - sent >= gather.chunk or export.frame == last - 1:
+                        gather.send_block(staging[sent:done])
+                        sent = done
                 elif self.exporting:
                     export.pipe(turbo=turbo)
                 elif on_frame is not None:
@@ -386,16 +396,19 @@ class ShaderScene(ShaderModule):
                 break
             prepare(export.frame)
 
-        if staging is not None:
+        if gather is not None:
             # the one exchange step of the path: finished frames → rank 0, in time order
-            index = 0
-            for block in D.FrameGather(export.total_frames, rank, world, chunk=16).stream(staging):
-                for frame in block:
-                    if export.pipe_handle is not None:
-                        export.pipe_handle.submit(frame.data_ptr())     # D2D into the ring, then D2H + write
-                    elif on_frame is not None:
-                        on_frame(index, frame.data_ptr())
-                    index += 1
+            if rank != 0:
+                gather.finish()
+            else:
+                index = last
+                for block in gather.drain():
+                    for frame in block:
+                        if export.pipe_handle is not None:
+                            export.pipe_handle.submit(frame.data_ptr())     # D2D into the ring, then D2H + write
+                        elif on_frame is not None:
+                            on_frame(index, frame.data_ptr())
+                        index += 1
             export.frame = export.total_frames
             self.cuda.sync()
         export.finish()

@@ -58,3 +58,44 @@ def test_gather_reassembles_frames_in_time_order(world, n_frames, chunk):
         assert p.exitcode == 0
     assert frames.shape == (n_frames, 4, 6, 3) and slowest == float(world)
     assert np.array_equal(frames[:, 0, 0, 0], np.arange(n_frames) % 251)
+
+
+def _overlap_worker(rank: int, world: int, port: int, n_frames: int, chunk: int, ahead: int, budget, out):
+    """The overlapped form scene.main uses: receives posted up front, blocks sent as they are finished"""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_range(n_frames, rank, world)
+    gather = FrameGather(n_frames, rank, world, chunk=chunk, ahead=ahead)
+    if rank == 0:
+        gather.post((4, 6, 3), torch.uint8, "cpu", budget_bytes=budget)
+        got = [torch.full((1, 4, 6, 3), k % 251, dtype=torch.uint8) for k in range(a, b)]      # its own frames
+        got += [blk.clone() for blk in gather.drain()]
+        out.put(torch.cat(got).numpy() if got else np.empty((0, 4, 6, 3), np.uint8))
+    else:
+        local = torch.stack([torch.full((4, 6, 3), k % 251, dtype=torch.uint8) for k in range(a, b)]) if b > a \
+            else torch.empty((0, 4, 6, 3), dtype=torch.uint8)
+        sent = 0
+        for done in range(1, b - a + 1):                       # "shade" one frame, send every finished block
+            if done - sent >= chunk or done == b - a:
+                gather.send_block(local[sent:done]); sent = done
+        gather.finish()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("budget", [None, 0], ids=["staged-rounds", "ring"])
+@pytest.mark.parametrize("world,n_frames,chunk,ahead", [(2, 21, 4, 2), (3, 50, 4, 3), (2, 5, 16, 8), (3, 2, 4, 1)])
+def test_overlapped_gather_keeps_time_order(world, n_frames, chunk, ahead, budget):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, n_frames, chunk, ahead, budget, out)) for r in range(world)]
+    for p in procs: p.start()
+    frames = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert frames.shape == (n_frames, 4, 6, 3)
+    assert np.array_equal(frames[:, 0, 0, 0], np.arange(n_frames) % 251)
