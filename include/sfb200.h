@@ -53,6 +53,10 @@ int         sfb_ctx_create(int device, void* stream, sfb_ctx** out);
 int         sfb_ctx_destroy(sfb_ctx* ctx);
 int         sfb_ctx_set_stream(sfb_ctx* ctx, void* stream);
 int         sfb_sync(sfb_ctx* ctx);                       /* blocks: cudaStreamSynchronize */
+/* Lets kernels of this ctx store into memory of `peer_device` (cudaDeviceEnablePeerAccess): the sharded
+ * export renders frames straight into rank 0's HBM over NVLink (no reference counterpart: the reference
+ * is single-GPU). Idempotent. */
+int         sfb_ctx_enable_peer(sfb_ctx* ctx, int peer_device);
 /* Kernel launches issued through this ctx since creation (bench.py's `gpu_launches`) */
 int         sfb_launch_count(sfb_ctx* ctx, uint64_t* count);
 

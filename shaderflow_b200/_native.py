@@ -76,6 +76,7 @@ _PROTOTYPES = dict(
     sfb_ctx_set_stream=(c_int, [c_void_p, c_void_p]),
     sfb_sync=(c_int, [c_void_p]),
     sfb_launch_count=(c_int, [c_void_p, POINTER(c_uint64)]),
+    sfb_ctx_enable_peer=(c_int, [c_void_p, c_int]),
     sfb_frame_clock=(c_int, [c_int, c_double, c_double, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     sfb_stft_mel=(c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int,
                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -285,6 +286,9 @@ class Context:
 
     def sync(self) -> None:
         check(lib().sfb_sync(self.handle))
+
+    def enable_peer(self, peer_device: int) -> None:
+        check(lib().sfb_ctx_enable_peer(self.handle, peer_device))
 
     @property
     def launches(self) -> int:

@@ -263,6 +263,8 @@ class ShaderAudio(BrokenAudio, ShaderModule):
             self.prepare()
         k = min(self.scene.frame_index, self.clock["frames"] - 1)
         self.tell = int(self.clock["tell"][k])
+        if not self.scene.render_enabled:
+            return                                   # a frame another rank shades: the tracks hold every frame's state
         row = self.scalars[k]
         # publish the GPU scan's state for this frame; the ShaderDynamics then only emit uniforms
         for dyn, value in ((self.volume, row[N.SCALAR_VOLUME]), (self.std, row[N.SCALAR_STD])):

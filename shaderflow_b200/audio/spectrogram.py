@@ -215,15 +215,17 @@ class ShaderSpectrogram(BrokenSpectrogram, ShaderModule):
         self._prepared_for = (self.config_key(), audio.clock["frames"])
 
     def update(self):
-        self.texture.components = self.audio.channels
-        self.texture.filter = ("linear" if self.smooth else "nearest")
-        self.texture.height = self.spectrogram_bins
-        self.texture.width = self.length_samples
+        tex = self.texture
+        want = (self.audio.channels, "linear" if self.smooth else "nearest", self.spectrogram_bins, self.length_samples)
+        if (tex.components, tex.filter.value, tex.height, tex.width) != want:
+            tex.components, tex.filter, tex.height, tex.width = want
         self.offset = (self.offset + 1) % self.length_samples
         if self.audio.clip is None or self.scene.cuda is None:
             return
         if self.columns is None or getattr(self, "_prepared_for", None) != (self.config_key(), self.scene.total_frames):
             self.prepare()
+        if not self.scene.render_enabled and self.length_samples == 1:
+            return                                   # a frame another rank shades (a scrolling texture still needs its column)
         k = min(self.scene.frame_index, self.columns.shape[0] - 1)
         row = self.columns[k]
         if self.length_samples == 1:

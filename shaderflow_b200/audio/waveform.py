@@ -86,6 +86,8 @@ class ShaderWaveform(ShaderModule):
             self.prepare()
         if self.texture.components != self.audio.channels:
             self.texture.components = self.audio.channels
+        if not self.scene.render_enabled:
+            return                                   # a frame another rank shades
         k = min(self.scene.frame_index, self.rows.shape[0] - 1)
         self.texture.bind(self.rows, self.rows[k].data_ptr())
 

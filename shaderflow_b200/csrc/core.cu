@@ -81,6 +81,19 @@ extern "C" int sfb_launch_count(sfb_ctx* ctx, uint64_t* count) {
     return SFB_OK;
 }
 
+extern "C" int sfb_ctx_enable_peer(sfb_ctx* ctx, int peer_device) {
+    SFB_REQUIRE(ctx, "sfb_ctx_enable_peer: null ctx");
+    if (peer_device == ctx->device) return SFB_OK;
+    SFB_CUDA(cudaSetDevice(ctx->device));
+    int can = 0;
+    SFB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) SFB_FAIL(SFB_ECUDA, "sfb_ctx_enable_peer: device %d cannot access device %d", ctx->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+    SFB_CUDA(e);
+    return SFB_OK;
+}
+
 int sfb_ctx_scratch(sfb_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
         SFB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -179,6 +179,69 @@ class FrameGather:
                 yield block
 
 
+class PeerFrames:
+    """Rank 0's staging for every remote frame, mapped into the other ranks over CUDA IPC so that they
+    shade STRAIGHT INTO rank 0's HBM: the frame kernel's rgb24 stores travel over NVLink as peer writes, the
+    exchange costs no kernel, no copy and no SM on either side, and it is complete when the shading is. What
+    is left of the collective is one barrier (NCCL) telling rank 0 that every shard has been written.
+
+    `negotiate` is collective over the group; it returns None on every rank when the mapping is not possible
+    (not CUDA/NCCL, staging over budget, IPC refused) and the export then uses FrameGather instead.
+    frames[k] is global frame `first_remote + k`."""
+
+    def __init__(self, frames: torch.Tensor, first_remote: int, keepalive=None):
+        self.frames, self.first_remote, self._keepalive = frames, first_remote, keepalive
+
+    def slot(self, frame: int) -> torch.Tensor:
+        return self.frames[frame - self.first_remote]
+
+    @staticmethod
+    def negotiate(n_frames: int, frame_shape, rank: int, world: int, device: int, group=None,
+                  budget_bytes: Optional[int] = None, enable_peer=None) -> Optional["PeerFrames"]:
+        import torch.distributed as dist
+        if world < 2 or not torch.cuda.is_available() or dist.get_backend(group) != "nccl" or os.environ.get("SFB_NO_PEER_FRAMES"):
+            return None
+        if budget_bytes is None:
+            budget_bytes = int(float(os.environ.get("SFB_PEER_BUDGET_GB", "96"))*(1 << 30))
+        _, first_remote = shard_range(n_frames, 0, world)
+        remote = n_frames - first_remote
+        frame_bytes = 1
+        for d in frame_shape:
+            frame_bytes *= int(d)
+        payload, frames, ok = [None], None, 1
+        if rank == 0:
+            try:
+                if remote*frame_bytes > budget_bytes:
+                    raise MemoryError("remote frames exceed the staging budget")
+                from torch.multiprocessing.reductions import reduce_tensor
+                frames = torch.empty((remote, *frame_shape), dtype=torch.uint8, device=f"cuda:{device}")
+                payload = [reduce_tensor(frames)]
+            except Exception:
+                frames, payload = None, [None]
+        dist.broadcast_object_list(payload, src=0, group=group)
+        if payload[0] is None:
+            ok = 0
+        elif rank != 0:
+            try:
+                rebuild, args = payload[0]
+                args = list(args)
+                owner = args[6]                            # device index of the exporting rank
+                if owner != device and enable_peer is not None:
+                    enable_peer(owner)                     # kernels on `device` may store into `owner`'s memory
+                if not os.environ.get("SFB_PEER_OPEN_ON_OWNER"):
+                    # map the allocation into THIS rank's device address space (cudaIpcOpenMemHandle maps into
+                    # the current device and enables peer access lazily); the tensor only serves as a pointer
+                    args[6] = device
+                frames = rebuild(*args)                    # a view of rank 0's memory in this process
+            except Exception:
+                frames, ok = None, 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return None
+        return PeerFrames(frames, first_remote)
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Timing rule: a multi-GPU duration is the max over ranks"""
     import torch.distributed as dist

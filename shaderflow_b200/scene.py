@@ -65,6 +65,11 @@ class ShaderScene(ShaderModule):
     fuse: bool = True
     """Use the fused K3+K4 kernel whenever final.glsl degenerates to a box filter"""
     _sink_ring: Any = None
+    _peer_frames: Any = None
+    """Sharded export: rank 0's staging of the remote frames, mapped into every rank (distributed.PeerFrames)"""
+    _peer_frames_key: Any = None
+    _updaters: Any = None
+    """(len(modules), modules whose update() runs every frame): rebuilt when a module is added"""
     """The frame sink's ring (pinned buffers, copy stream, writer thread), kept across main() calls"""
     kernel_events: Any = None
     """When a list: (start, end) torch CUDA events are appended around every shading launch (bench.py)"""
@@ -293,17 +298,21 @@ class ShaderScene(ShaderModule):
 
     def next(self, dt: float = 0.0) -> None:
         """Update all modules, render, then integrate time (so frame 0 sees time=0, dt=0)"""
-        for module in self.modules:
-            if not isinstance(module, ShaderProgram):
-                module.update()
+        updaters = self._updaters
+        if updaters is None or updaters[0] != len(self.modules):
+            updaters = self._updaters = (len(self.modules), [m for m in self.modules if not isinstance(m, ShaderProgram)])
+        for module in updaters[1]:
+            module.update()
         if self.render_enabled and self.cuda is not None:
             self.render()
         if self.vsync is not None:
             self.vsync.fps = self.fps
-        self.dt = dt*self.speed
-        self.rdt = dt
-        self.time += self.dt
-        self.frame_index += 1
+        # plain stores: these four are written once per frame (the attrs converters are for user input)
+        store = object.__setattr__
+        store(self, "dt", float(dt*self.speed))
+        store(self, "rdt", float(dt))
+        store(self, "time", self.time + self.dt)
+        store(self, "frame_index", self.frame_index + 1)
 
     def main(self, *, width: Optional[int] = 1920, height: Optional[int] = 1080, scale: float = 1.0,
              ratio=None, fps: float = 60.0, frameskip: bool = True, fullscreen: bool = False,
@@ -354,23 +363,33 @@ class ShaderScene(ShaderModule):
         if rank == 0:
             export.open_bar()
         first, last = frames if frames is not None else (0, export.total_frames)
-        staging, gather, sent = None, None, 0
+        staging, gather, peer, sent = None, None, None, 0
         if sharded:
-            # Rank 0 treats its own range like a single-GPU export (frames go straight to the sink ring) and
-            # has the receives of the other ranks' blocks posted before it starts shading; the other ranks
-            # shade into HBM and send each finished block without waiting (distributed.FrameGather).
+            # Rank 0 treats its own range like a single-GPU export (frames go straight to the sink ring).
+            # The other ranks shade straight into rank 0's HBM over NVLink when CUDA IPC allows it
+            # (distributed.PeerFrames); otherwise they shade into their own HBM and send each finished block
+            # without waiting, rank 0 having posted the receives before it starts (distributed.FrameGather).
             import torch
             first, last = D.shard_range(export.total_frames, rank, world)
-            gather = D.FrameGather(export.total_frames, rank, world, chunk=4)
-            if rank == 0:
-                gather.post((self.height, self.width, 3), torch.uint8, f"cuda:{self.device}")
-            else:
-                staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
+            key = (export.total_frames, self.height, self.width, world)
+            if getattr(self, "_peer_frames_key", None) != key:
+                self._peer_frames = D.PeerFrames.negotiate(export.total_frames, (self.height, self.width, 3), rank, world, self.device,
+                                                              enable_peer=self.cuda.enable_peer)
+                self._peer_frames_key = key
+            peer = self._peer_frames
+            if peer is None:
+                gather = D.FrameGather(export.total_frames, rank, world, chunk=4)
+                if rank == 0:
+                    gather.post((self.height, self.width, 3), torch.uint8, f"cuda:{self.device}")
+                else:
+                    staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
 
         def prepare(index: int) -> None:
             """Decides, before frame `index` is stepped, whether it is shaded and where to"""
             self.render_enabled = (first <= index < last)
-            if staging is not None:
+            if peer is not None and rank != 0:
+                self._frame_target = peer.slot(index).data_ptr() if self.render_enabled else None
+            elif staging is not None:
                 self._frame_target = staging[index - first].data_ptr() if self.render_enabled else None
             else:
                 self._frame_target = export.target() if (self.exporting and self.render_enabled) else None
@@ -382,7 +401,9 @@ class ShaderScene(ShaderModule):
             if task is not self.vsync:
                 continue
             if self.render_enabled:
-                if staging is not None:
+                if peer is not None and rank != 0:
+                    pass                                      # the kernel stored the frame into rank 0's HBM
+                elif staging is not None:
                     done = export.frame - first + 1            # frames of the shard shaded so far
                     if done - sent >= gather.chunk or export.frame == last - 1:
                         gather.send_block(staging[sent:done])
@@ -396,13 +417,19 @@ class ShaderScene(ShaderModule):
                 break
             prepare(export.frame)
 
-        if gather is not None:
+        if sharded:
             # the one exchange step of the path: finished frames → rank 0, in time order
+            if peer is not None:
+                import torch.distributed as dist
+                self.cuda.sync()                              # this rank's peer writes have landed
+                dist.barrier()                                # ... and so have everybody's
             if rank != 0:
-                gather.finish()
+                if gather is not None:
+                    gather.finish()
             else:
                 index = last
-                for block in gather.drain():
+                blocks = gather.drain() if gather is not None else (peer.frames[a:a + 16] for a in range(0, peer.frames.shape[0], 16))
+                for block in blocks:
                     for frame in block:
                         if export.pipe_handle is not None:
                             export.pipe_handle.submit(frame.data_ptr())     # D2D into the ring, then D2H + write
@@ -411,6 +438,8 @@ class ShaderScene(ShaderModule):
                         index += 1
             export.frame = export.total_frames
             self.cuda.sync()
+            if peer is not None:
+                dist.barrier()                                # the staging may be written again only now
         export.finish()
         result = export.result()
         export.log_stats(output=result)
