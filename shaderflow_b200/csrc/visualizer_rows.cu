@@ -258,6 +258,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             const int ry1 = int(floorf(hi + scale*1.0001f)) + 1;                 // last texel row touched
             const int nq = (ry1 - ry0 + 4) >> 2;
             if (ry0 < 0 || nq < 1 || nq > VR_MAXQ || ry0 + 4*nq > win_h) { bad = 1; continue; }
+            if (row >= 4*nq) continue;                                           // phase 1 never reads these
             const float cy = cyS[g][r] - y0f - float(ry0 + row);
             float w = 0.0f;
             #pragma unroll 7
@@ -422,8 +423,22 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         sc.texels = column ? reinterpret_cast<const float2*>(sp.lin) : nullptr; sc.h = sp.h; sc.ry = sp.ry;
     }
     const float agx = vc.f.agluv.x, asx = vc.f.astuv.x, uvx = vc.uv.x;
-    float wavx, wavy;
-    { const vec4 w = texture<false>(P.tex[2], mk2(asx, 0.0f)); wavx = 0.2f*w.x; wavy = 0.2f*w.y; }
+    float wavx, wavy;                                              // 0.2*texture(iWaveform, (astuv.x, 0)): per column
+    {
+        const DevSampler& wv = P.tex[2];
+        if (wv.dtype == SFB_DTYPE_F32 && wv.padded == 2 && wv.h == 1 && wv.filter == SFB_FILTER_LINEAR && !wv.rx) {
+            // the usual RG32F row, LINEAR + CLAMP_TO_EDGE (waveform.py:64-87): same arithmetic as texture<false>
+            const float ub = asx*float(wv.w) - 0.5f, fx = floorf(ub), a = ub - fx;
+            const int i0 = min(max(int(fx), 0), wv.w - 1), i1 = min(max(int(fx) + 1, 0), wv.w - 1);
+            const float2 t0 = __ldg(reinterpret_cast<const float2*>(wv.lin) + i0), t1 = __ldg(reinterpret_cast<const float2*>(wv.lin) + i1);
+            // rows j0 and j0 + 1 are the same texel row (h == 1): top*(1 - b) + bot*b with top == bot
+            const float b = (0.0f*1.0f - 0.5f) - floorf(0.0f*1.0f - 0.5f);
+            const float tx_ = t0.x*(1.0f - a) + t1.x*a, ty_ = t0.y*(1.0f - a) + t1.y*a;
+            wavx = 0.2f*(tx_*(1.0f - b) + tx_*b); wavy = 0.2f*(ty_*(1.0f - b) + ty_*b);
+        } else {
+            const vec4 w = texture<false>(wv, mk2(asx, 0.0f)); wavx = 0.2f*w.x; wavy = 0.2f*w.y;
+        }
+    }
     // two fragments in flight per iteration (the back end is a long dependent chain)
     #pragma unroll (S == 1 ? 2 : 1)
     for (int pr = 0; pr < J/S; pr++) {
