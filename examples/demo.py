@@ -17,7 +17,9 @@ import shaderflow_b200
 shaderflow_b200.install_alias()
 
 from shaderflow.scene import ShaderScene          # noqa: E402
+from shaderflow.shader import ShaderProgram       # noqa: E402
 from shaderflow.texture import ShaderTexture      # noqa: E402
+from shaderflow.variable import Uniform           # noqa: E402
 
 shaders: Path = (Path(__file__).parent/"shaders")
 
@@ -37,6 +39,94 @@ class ShaderToy(ShaderScene):
     """ShaderToy Default Shader"""
     def build(self):
         self.shader.fragment = (shaders/"shadertoy.frag")
+
+
+class MultiShader(ShaderScene):
+    """Basic scene with two shaders acting together"""
+    def build(self):
+        self.child = ShaderProgram(scene=self, name="child")
+        # Left screen is green, right screen is black (inline GLSL of the reference, selected by directive here)
+        self.child.fragment = ("// sfb200: scene=multishader_child")
+        # Left screen is black, right screen is red; adds the content of the child shader
+        self.shader.fragment = ("// sfb200: scene=multishader")
+
+
+class Multipass(ShaderScene):
+    """Multi layers done on a single shader"""
+    background = None
+
+    def build(self):
+        image = self.background if self.background is not None else synthetic_background()
+        ShaderTexture(scene=self, name="background").from_image(image)
+        self.shader.texture.layers = 2
+        self.shader.fragment = (shaders/"multipass.frag")
+
+
+class MotionBlur(ShaderScene):
+    """Poor's man Motion Blur"""
+    background = None
+
+    def build(self):
+        image = self.background if self.background is not None else synthetic_background()
+        ShaderTexture(scene=self, name="background").from_image(image)
+        self.shader.texture.temporal = 10
+        self.shader.texture.layers = 2
+        self.shader.fragment = (shaders/"motionblur.frag")
+
+
+class Dynamics(ShaderScene):
+    """Second order system"""
+    background = None
+
+    def build(self):
+        from shaderflow.dynamics import ShaderDynamics
+        image = self.background if self.background is not None else synthetic_background()
+        ShaderTexture(scene=self, name="background").from_image(image)
+        self.dynamics = ShaderDynamics(scene=self, name="iShaderDynamics", frequency=4)
+        self.shader.fragment = ("// sfb200: scene=dynamics")
+
+    def update(self):
+        import math
+        # This is how square waves are born in the digital world
+        self.dynamics.target = 0.5*(1 + np.sign(np.sin(2*math.pi*self.time*0.5)))
+
+
+class Audio(ShaderScene):
+    """Basic audio processing (the reference opens a soundcard recorder; here a clip is loaded)"""
+    def build(self):
+        from shaderflow.audio import ShaderAudio
+        self.audio = ShaderAudio(scene=self, name="iAudio")
+        self.shader.fragment = ("// sfb200: scene=audio")
+
+
+class Life(ShaderScene):
+    """Conway's Game of Life in GLSL"""
+    life_period: int = 6
+    """Number of frames between each life update"""
+    life_seed = None
+    """Seed of the initial state (the reference draws it from numpy's global generator)"""
+
+    def setup(self):
+        width, height = 192, 108
+        rng = np.random.default_rng(self.life_seed) if self.life_seed is not None else np.random
+        random = (rng.integers(0, 2, (width, height)) if self.life_seed is not None
+                  else rng.randint(0, 2, (width, height))).astype(bool)
+        self.simulation.texture.size = (width, height)
+        self.simulation.texture.write(random.astype(np.float32), temporal=1)
+
+    def build(self):
+        self.simulation = ShaderProgram(scene=self, name="iLife")
+        self.simulation.texture.temporal = 10
+        self.simulation.texture.filter = "nearest"
+        self.simulation.texture.dtype = "f4"
+        self.simulation.texture.components = 1
+        self.simulation.texture.track = False
+        self.simulation.fragment = (shaders/"life"/"simulation.glsl")
+        self.shader.fragment = (shaders/"life"/"visuals.glsl")
+
+    def pipeline(self):
+        yield from ShaderScene.pipeline(self)
+        yield Uniform("int", "iLifePeriod", self.life_period)
 
 
 class Waveform(ShaderScene):

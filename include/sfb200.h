@@ -159,11 +159,20 @@ enum {
     SFB_SCENE_MANDELBROT = 5,  /* examples/fractals/shaders/mandelbrot.frag    (Mandelbrot) */
     SFB_SCENE_TETRATION = 6,   /* examples/fractals/shaders/tetration.frag     (Tetration)  */
     SFB_SCENE_RAYMARCH = 7,    /* examples/basic/shaders/raymarch.frag         (RayMarch)   */
-    SFB_SCENE_COUNT = 8,
+    /* multi-program / multi-layer / temporal scenes */
+    SFB_SCENE_MULTISHADER_CHILD = 8,  /* examples/basic/demo.py:74-79, inline      (MultiShader.child)  */
+    SFB_SCENE_MULTISHADER = 9,        /* examples/basic/demo.py:83-89, inline      (MultiShader)        */
+    SFB_SCENE_MULTIPASS = 10,         /* examples/basic/shaders/multipass.frag     (Multipass, 2 layers) */
+    SFB_SCENE_MOTIONBLUR = 11,        /* examples/basic/shaders/motionblur.frag    (MotionBlur, temporal) */
+    SFB_SCENE_DYNAMICS = 12,          /* examples/basic/demo.py:120-125, inline    (Dynamics)           */
+    SFB_SCENE_AUDIO = 13,             /* examples/basic/demo.py:150-154, inline    (Audio)              */
+    SFB_SCENE_LIFE_SIMULATION = 14,   /* examples/basic/shaders/life/simulation.glsl (Life.simulation)  */
+    SFB_SCENE_LIFE_VISUALS = 15,      /* examples/basic/shaders/life/visuals.glsl  (Life)               */
+    SFB_SCENE_COUNT = 16,
 };
 
 #define SFB_MAX_EXTRA 16
-#define SFB_MAX_SAMPLERS 8
+#define SFB_MAX_SAMPLERS 20
 
 /* One POD block passed by value to the kernel (__grid_constant__): the uniforms of
  * ShaderScene.pipeline (scene.py:687-703), ShaderCamera.pipeline + its ShaderDynamics (camera.py:146-201),
@@ -187,6 +196,8 @@ typedef struct sfb_scene_info {
     const char* reference;                  /* reference file the kernel transliterates */
     int n_extra;    const char* extra[SFB_MAX_EXTRA];       /* uniform names → extra[i] slots */
     int n_samplers; const char* samplers[SFB_MAX_SAMPLERS]; /* sampler2D names → samplers[i] */
+    int n_required;                         /* the first n_required samplers must be bound; the rest are the  */
+                                            /* history of a temporal texture, as deep as the scene made it     */
 } sfb_scene_info;
 
 int sfb_scene_lookup(const char* name, int* scene);       /* SFB_ENOTFOUND when not built in */
@@ -208,6 +219,12 @@ enum {
 int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
                       sfb_tex* const* samplers, int n_samplers, int flags,
                       int target_w, int target_h, void* dst_rgba8_dev, float* dst_f32_dev);
+
+/* The same pass into a texture's own storage, in the texture's format (u8 or f32, 1-4 components): the FBO
+ * render of a child program / a layer / a temporal slot (shader.py:398-405, texture.py:266-267). The target
+ * then samples through the exact path until the next sfb_tex_write. iResolution comes from `uniforms`. */
+int sfb_render_target(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                      sfb_tex* const* samplers, int n_samplers, int flags, sfb_tex* target);
 
 /* Final pass (K4): fragment/final.glsl:3-33 over an RGBA8 iScreen (LINEAR, CLAMP_TO_EDGE) into a
  * width x height target with `components` 3 (rgb24, what ffmpeg gets: exporting.py:94-103) or 4. */

@@ -9,7 +9,9 @@ numpy float32 restatement of the reference's GLSL render path, one array lane pe
     camera                        shaderflow/resources/shaders/include/camera.glsl:55-155
     SSAA downsample               shaderflow/resources/shaders/fragment/final.glsl:3-33
     scenes                        fragment/default.glsl, examples/basic/shaders/{visualizer,bars,waveform,
-                                  shadertoy,raymarch}.frag, examples/fractals/shaders/{mandelbrot,tetration}.frag
+                                  shadertoy,raymarch,multipass,motionblur}.frag, life/{simulation,visuals}.glsl,
+                                  the inline GLSL of examples/basic/demo.py (MultiShader, Dynamics, Audio),
+                                  examples/fractals/shaders/{mandelbrot,tetration}.frag
     texture formats / filters     shaderflow/texture.py:28-38,104-137,175-182,327-338
     render / readback conventions shaderflow/shader.py:367-405, scene.py:185-194, exporting.py:94-103,165-174
 
@@ -204,6 +206,7 @@ class Uniforms:
     iSSAA: float = 1.0
     iFramerate: float = 60.0
     iFrame: int = 0
+    iLayer: int = 0
     iCameraMode: int = 1
     iCameraProjection: int = 0
     iCameraPosition: tuple = (0.0, 0.0, 0.0)
@@ -511,9 +514,146 @@ def frag_raymarch(u: Uniforms, f: Frag, tex: dict):
     return np.stack([col, col, col, np.ones_like(col)], -1)
 
 
+# ---------------------------------------------------------------------------------------------- #
+# Multi-program / multi-layer / temporal scenes of examples/basic/demo.py. A program renders
+# each layer l of its texture with iLayer = l (shader.py:398-405); `X{t}x{l}` names the texture of t frames
+# ago, layer l (texture.py:354-368); the program's own texture is RGBA8 unless the scene says otherwise.
+
+def _opaque(rgb):
+    return np.concatenate([rgb.astype(F), np.ones(rgb.shape[:-1] + (1,), F)], -1)
+
+
+def frag_multishader_child(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/demo.py:74-79 (inline GLSL of MultiShader.child)"""
+    z = np.zeros_like(f.stuv[..., 0])
+    return _opaque(vec(z, (F(1) - f.stuv[..., 0]).astype(F), z))
+
+
+def frag_multishader(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/demo.py:83-89 (inline GLSL of MultiShader.shader)"""
+    z = np.zeros_like(f.stuv[..., 0])
+    rgb = (vec(f.stuv[..., 0], z, z) + tex["child"].sample(f.astuv)[..., :3]).astype(F)
+    return _opaque(rgb)
+
+
+def _blur(image: Texture, stuv, radius: float, directions: int, steps: int):
+    """multipass.frag:11-26 with its float loop counters evaluated in strict float32"""
+    color = np.zeros(stuv.shape[:-1] + (4,), F)
+    weights = F(0.0)
+    direction, dstep, wstep = F(0.0), F(TAU/F(directions)), F(F(1.0)/F(steps))
+    while direction < TAU:
+        d = vec(np.cos(direction), np.sin(direction))
+        walk = wstep
+        while walk < F(1.0):
+            offset = (((d*F(radius)).astype(F)*walk).astype(F)/F(2000)).astype(F)
+            sample = image.sample((stuv + offset).astype(F))
+            weight = F(F(1.0) - length(offset)/F(radius))
+            color = (color + sample*weight).astype(F)
+            weights = F(weights + weight)
+            walk = F(walk + wstep)
+        direction = F(direction + dstep)
+    return (color/weights).astype(F)
+
+
+def frag_multipass(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/shaders/multipass.frag:28-47"""
+    if u.iLayer == 0:
+        out = stexture(tex["background"], f.stuv)
+    else:
+        screen = tex["iScreen0x0"]
+        out = screen.sample(f.astuv)
+        left = out.copy(); left[..., 0] = F(1) - left[..., 0]
+        out = np.where((f.gluv[..., 0] < 0)[..., None], left, _blur(screen, f.astuv, 5.0, 8, 8))
+    out = out.astype(F).copy(); out[..., 3] = F(1)
+    return out
+
+
+def frag_motionblur(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/shaders/motionblur.frag:1-18; extra: iScreenTemporal"""
+    cam = get_camera(u, f)
+    if u.iLayer == 0:
+        out = stexture(tex["background"], cam.stuv)
+    else:
+        T = int(u.extra["iScreenTemporal"])
+        color = np.zeros(f.astuv.shape[:-1] + (4,), F)
+        for i in range(T):
+            factor = smoothstep(1.0, 0.0, F(i)/F(T))
+            color = (color + tex[f"iScreen{i}x0"].sample(f.astuv)*factor).astype(F)
+        out = ((F(2)*color)/F(T)).astype(F)
+    out = out.astype(F).copy(); out[..., 3] = F(1)
+    return out
+
+
+def frag_dynamics(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/demo.py:120-125 (inline GLSL of Dynamics); extra: iShaderDynamics"""
+    z = F(F(0.85) + F(0.1)*F(u.extra["iShaderDynamics"]))
+    return stexture(tex["background"], zoom(f.stuv, np.full(f.stuv.shape[:-1], z, F), vec(F(0.5), F(0.5))))
+
+
+def frag_audio(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/demo.py:150-154 (inline GLSL of Audio); extra: iAudioVolume"""
+    v = np.full(f.stuv.shape[:-1], F(u.extra["iAudioVolume"]), F)
+    return _opaque(vec(v, v, v))
+
+
+LIFE_ALIVE = np.array([0, 0, 1, 1, 0, 0, 0, 0, 0], np.int32)    # life/simulation.glsl:7-11
+LIFE_DEAD = np.array([0, 0, 0, 1, 0, 0, 0, 0, 0], np.int32)     # :14-18
+
+
+def texel_fetch(tex: Texture, ix, iy):
+    """texelFetch(sampler, ivec2, 0): no filtering, no wrapping; a fetch outside the image is undefined in
+    GLSL 3.30 — fixed here as zeros (what robust buffer access returns)"""
+    H, W, _ = tex.data.shape
+    inside = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+    t = tex.data[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)].astype(F)
+    if tex.data.dtype == np.uint8:
+        t = t/F(255)
+    return np.where(inside[..., None], t, F(0))
+
+
+def frag_life_simulation(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/shaders/life/simulation.glsl:20-50; extra: iLifePeriod, iLifeSize. Writes .r"""
+    prev = tex["iLife1x0"]
+    if (int(u.iFrame) % int(u.extra["iLifePeriod"])) != 0:
+        r = prev.sample(f.astuv)[..., 0]
+    else:
+        size = np.asarray(u.extra["iLifeSize"], F)
+        pixel = (f.astuv*size).astype(F).astype(np.int64)            # ivec2(): truncation
+        near = np.zeros(pixel.shape[:-1], np.int32)
+        current = np.zeros(pixel.shape[:-1], np.int32)
+        for x in (-1, 0, 1):
+            for y in (-1, 0, 1):
+                cell = (texel_fetch(prev, pixel[..., 0] + x, pixel[..., 1] + y)[..., 0] > F(0.5)).astype(np.int32)
+                if x == 0 and y == 0:
+                    current = cell
+                else:
+                    near = near + cell
+        r = np.where(current == 1, LIFE_ALIVE[near], LIFE_DEAD[near]).astype(F)
+    z = np.zeros_like(r)
+    return np.stack([r, z, z, np.ones_like(r)], -1).astype(F)
+
+
+def frag_life_visuals(u: Uniforms, f: Frag, tex: dict):
+    """examples/basic/shaders/life/visuals.glsl:11-38"""
+    cam = get_camera(u, f)
+    uv = cam.stuv
+    exponent = F(1.3)
+    area = F(F(1)/(exponent + F(1)))
+    life = stexture(tex["iLife0x0"], uv)[..., 0]
+    for k, base in ((1, 0.8), (2, 0.6), (3, 0.4), (4, 0.2)):
+        life = (life + stexture(tex[f"iLife{k}x0"], uv)[..., 0]*gpow(F(base), exponent)).astype(F)
+    life = (life/(F(5)*area)).astype(F)
+    rgb = palette(life, *MAGMA)
+    rgb = np.where(cam.out_of_bounds[..., None], np.asarray(MAGMA[0], F), rgb)
+    return _opaque(rgb)
+
+
 SCENES = dict(
     default=frag_default, shadertoy=frag_shadertoy, visualizer=frag_visualizer, bars=frag_bars,
     waveform=frag_waveform, mandelbrot=frag_mandelbrot, tetration=frag_tetration, raymarch=frag_raymarch,
+    multishader_child=frag_multishader_child, multishader=frag_multishader, multipass=frag_multipass,
+    motionblur=frag_motionblur, dynamics=frag_dynamics, audio=frag_audio,
+    life_simulation=frag_life_simulation, life_visuals=frag_life_visuals,
 )
 
 # ---------------------------------------------------------------------------------------------- #

@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIBRARY = Path(__file__).resolve().parent/"libsfb200.so"
 
-MAX_EXTRA, MAX_SAMPLERS = 16, 8
+MAX_EXTRA, MAX_SAMPLERS = 16, 20
 OK, EINVAL, ECUDA, ENOTFOUND, ENOMEM, EIO, ESTATE = 0, -1, -2, -3, -4, -5, -6
 WINDOW = dict(hanning=0, hann_poisson=1, none=2)
 MAGNITUDE = dict(power=0, amplitude=1)
@@ -22,6 +22,7 @@ DTYPE_U8, DTYPE_F32, DTYPE_F16 = 0, 1, 2
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
 FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL, RENDER_TILED = 0, 1, 2, 4
 SCALARS = 5
+SCENE_COUNT = 16
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
 
 
@@ -64,6 +65,7 @@ class SceneInfo(C.Structure):
         ("name", c_char_p), ("reference", c_char_p),
         ("n_extra", c_int), ("extra", c_char_p*MAX_EXTRA),
         ("n_samplers", c_int), ("samplers", c_char_p*MAX_SAMPLERS),
+        ("n_required", c_int),
     ]
 
 
@@ -94,6 +96,7 @@ _PROTOTYPES = dict(
     sfb_scene_info_get=(c_int, [c_int, POINTER(SceneInfo)]),
     sfb_render_screen=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
                                c_int, c_int, c_void_p, c_void_p]),
+    sfb_render_target=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int, c_void_p]),
     sfb_render_final=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_render_frame=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -177,6 +180,7 @@ def scene_info(scene: int) -> dict:
         name=info.name.decode(), reference=info.reference.decode(),
         extra=[info.extra[i].decode() for i in range(info.n_extra)],
         samplers=[info.samplers[i].decode() for i in range(info.n_samplers)],
+        required=info.n_required,
     )
 
 
@@ -325,6 +329,11 @@ class Context:
                       dst_f32=None, flags: int = FILTER_EXACT) -> None:
         arr, n = self._samplers(textures)
         check(lib().sfb_render_screen(self.handle, scene, byref(uniforms), arr, n, flags, width, height, _ptr(dst), _ptr(dst_f32)))
+
+    def render_target(self, scene: int, uniforms: Uniforms, textures, target: "Texture", flags: int = FILTER_EXACT) -> None:
+        """The scene's pass into `target`'s own storage, in its format (a child program / layer / temporal slot)"""
+        arr, n = self._samplers(textures)
+        check(lib().sfb_render_target(self.handle, scene, byref(uniforms), arr, n, flags, target.handle))
 
     def render_final(self, screen, screen_w: int, screen_h: int, width: int, height: int,
                      subsample: int, components: int, dst) -> None:

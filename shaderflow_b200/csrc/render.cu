@@ -24,8 +24,18 @@ __global__ void __launch_bounds__(256) screen_kernel(const __grid_constant__ Ren
     const Frag f = make_frag(P, i, j);
     const vec4 c = shade<SCENE, HW>(P, f);
     const size_t idx = size_t(j)*size_t(P.Wr) + size_t(i);
-    reinterpret_cast<uchar4*>(P.dst)[idx] =
-        make_uchar4(to_unorm8(c.x), to_unorm8(c.y), to_unorm8(c.z), to_unorm8(c.w));
+    if (P.dst_dtype == SFB_DTYPE_U8 && P.dst_padded == 4) {
+        reinterpret_cast<uchar4*>(P.dst)[idx] =
+            make_uchar4(to_unorm8(c.x), to_unorm8(c.y), to_unorm8(c.z), to_unorm8(c.w));
+    } else {
+        // a texture of another format as the colour attachment (sfb_render_target): its stored components
+        const float comp[4] = {c.x, c.y, c.z, c.w};
+        for (int k = 0; k < P.dst_padded; k++) {
+            if (P.dst_dtype == SFB_DTYPE_U8)       P.dst[idx*size_t(P.dst_padded) + k] = (unsigned char)to_unorm8(comp[k]);
+            else if (P.dst_dtype == SFB_DTYPE_F32) reinterpret_cast<float*>(P.dst)[idx*size_t(P.dst_padded) + k] = comp[k];
+            else                                   reinterpret_cast<__half*>(P.dst)[idx*size_t(P.dst_padded) + k] = __float2half_rn(comp[k]);
+        }
+    }
     if (P.dst_f32) reinterpret_cast<float4*>(P.dst_f32)[idx] = make_float4(c.x, c.y, c.z, c.w);
 }
 
@@ -161,15 +171,27 @@ extern "C" int sfb_tex_sample(sfb_tex* tex, const float* uv_dev, int n, int flag
 // Scene registry
 
 static const sfb_scene_info SCENES[SFB_SCENE_COUNT] = {
-    {"default",    "shaderflow/resources/shaders/fragment/default.glsl", 0, {}, 0, {}},
-    {"shadertoy",  "examples/basic/shaders/shadertoy.frag",               0, {}, 0, {}},
+    {"default",    "shaderflow/resources/shaders/fragment/default.glsl", 0, {}, 0, {}, 0},
+    {"shadertoy",  "examples/basic/shaders/shadertoy.frag",               0, {}, 0, {}, 0},
     {"visualizer", "examples/basic/shaders/visualizer.frag", 2, {"iAudioVolume", "iAudioSTD"},
-                   3, {"background", "iSpectrogram", "iWaveform"}},
-    {"bars",       "examples/basic/shaders/bars.frag",      0, {}, 1, {"iSpectrogram"}},
-    {"waveform",   "examples/basic/shaders/waveform.frag",  0, {}, 1, {"iWaveform"}},
-    {"mandelbrot", "examples/fractals/shaders/mandelbrot.frag", 0, {}, 0, {}},
-    {"tetration",  "examples/fractals/shaders/tetration.frag",  0, {}, 0, {}},
-    {"raymarch",   "examples/basic/shaders/raymarch.frag",      0, {}, 0, {}},
+                   3, {"background", "iSpectrogram", "iWaveform"}, 3},
+    {"bars",       "examples/basic/shaders/bars.frag",      0, {}, 1, {"iSpectrogram"}, 1},
+    {"waveform",   "examples/basic/shaders/waveform.frag",  0, {}, 1, {"iWaveform"}, 1},
+    {"mandelbrot", "examples/fractals/shaders/mandelbrot.frag", 0, {}, 0, {}, 0},
+    {"tetration",  "examples/fractals/shaders/tetration.frag",  0, {}, 0, {}, 0},
+    {"raymarch",   "examples/basic/shaders/raymarch.frag",      0, {}, 0, {}, 0},
+    {"multishader_child", "examples/basic/demo.py:74-79",       0, {}, 0, {}, 0},
+    {"multishader", "examples/basic/demo.py:83-89",             0, {}, 1, {"child"}, 1},
+    {"multipass",  "examples/basic/shaders/multipass.frag",     0, {}, 2, {"background", "iScreen0x0"}, 2},
+    {"motionblur", "examples/basic/shaders/motionblur.frag",    1, {"iScreenTemporal"},
+                   17, {"background", "iScreen0x0", "iScreen1x0", "iScreen2x0", "iScreen3x0", "iScreen4x0", "iScreen5x0",
+                        "iScreen6x0", "iScreen7x0", "iScreen8x0", "iScreen9x0", "iScreen10x0", "iScreen11x0",
+                        "iScreen12x0", "iScreen13x0", "iScreen14x0", "iScreen15x0"}, 2},
+    {"dynamics",   "examples/basic/demo.py:120-125",            1, {"iShaderDynamics"}, 1, {"background"}, 1},
+    {"audio",      "examples/basic/demo.py:150-154",            1, {"iAudioVolume"}, 0, {}, 0},
+    {"life_simulation", "examples/basic/shaders/life/simulation.glsl", 2, {"iLifePeriod", "iLifeSize"}, 1, {"iLife1x0"}, 1},
+    {"life_visuals", "examples/basic/shaders/life/visuals.glsl", 0, {},
+                   5, {"iLife0x0", "iLife1x0", "iLife2x0", "iLife3x0", "iLife4x0"}, 5},
 };
 
 extern "C" int sfb_scene_lookup(const char* name, int* scene) {
@@ -216,8 +238,12 @@ static int fill_params(RenderParams& P, const char* who, int scene, const sfb_un
                        sfb_tex* const* samplers, int n_samplers, int flags) {
     SFB_REQUIRE(scene >= 0 && scene < SFB_SCENE_COUNT, "%s: bad scene %d", who, scene);
     SFB_REQUIRE(uniforms, "%s: null uniforms", who);
-    SFB_REQUIRE(n_samplers >= SCENES[scene].n_samplers && n_samplers <= SFB_MAX_SAMPLERS,
-        "%s: scene '%s' needs %d samplers, got %d", who, SCENES[scene].name, SCENES[scene].n_samplers, n_samplers);
+    SFB_REQUIRE(n_samplers >= SCENES[scene].n_required && n_samplers <= SFB_MAX_SAMPLERS,
+        "%s: scene '%s' needs %d samplers, got %d", who, SCENES[scene].name, SCENES[scene].n_required, n_samplers);
+    if (scene == SFB_SCENE_MOTIONBLUR)
+        SFB_REQUIRE(n_samplers >= 1 + int(uniforms->extra[0][0]),
+            "%s: motionblur averages iScreenTemporal = %d frames but only %d history samplers are bound",
+            who, int(uniforms->extra[0][0]), n_samplers - 1);
     P.u = *uniforms;
     for (int i = 0; i < n_samplers; i++) {
         SFB_REQUIRE(samplers && samplers[i], "%s: sampler %d is null", who, i);
@@ -243,6 +269,9 @@ static void dispatch(int scene, bool hw, A... a) {
         SFB_CASE(SFB_SCENE_DEFAULT) SFB_CASE(SFB_SCENE_SHADERTOY) SFB_CASE(SFB_SCENE_VISUALIZER)
         SFB_CASE(SFB_SCENE_BARS) SFB_CASE(SFB_SCENE_WAVEFORM) SFB_CASE(SFB_SCENE_MANDELBROT)
         SFB_CASE(SFB_SCENE_TETRATION) SFB_CASE(SFB_SCENE_RAYMARCH)
+        SFB_CASE(SFB_SCENE_MULTISHADER_CHILD) SFB_CASE(SFB_SCENE_MULTISHADER) SFB_CASE(SFB_SCENE_MULTIPASS)
+        SFB_CASE(SFB_SCENE_MOTIONBLUR) SFB_CASE(SFB_SCENE_DYNAMICS) SFB_CASE(SFB_SCENE_AUDIO)
+        SFB_CASE(SFB_SCENE_LIFE_SIMULATION) SFB_CASE(SFB_SCENE_LIFE_VISUALS)
     }
     #undef SFB_CASE
 }
@@ -313,8 +342,28 @@ extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.W = int(uniforms->iResolution[0]); P.H = int(uniforms->iResolution[1]);
     P.inv_Wr = 1.0/double(target_w); P.inv_Hr = 1.0/double(target_h);
     P.dst = static_cast<unsigned char*>(dst_rgba8_dev); P.dst_f32 = dst_f32_dev;
+    P.dst_dtype = SFB_DTYPE_U8; P.dst_padded = 4;
     dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+extern "C" int sfb_render_target(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                                 sfb_tex* const* samplers, int n_samplers, int flags, sfb_tex* target) {
+    SFB_REQUIRE(ctx && target, "sfb_render_target: null ctx or target");
+    SFB_REQUIRE(!target->external && target->lin, "sfb_render_target: the target has no storage of its own");
+    // The target may also be in `samplers` (a layer-0 pass of multipass.frag binds iScreen0x0 without reading
+    // it): like GL, that is only undefined if the pass actually samples it.
+    RenderParams P{};
+    if (int e = fill_params(P, "sfb_render_target", scene, uniforms, samplers, n_samplers, flags)) return e;
+    P.Wr = target->w; P.Hr = target->h;
+    P.W = int(uniforms->iResolution[0]); P.H = int(uniforms->iResolution[1]);
+    P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
+    P.dst = static_cast<unsigned char*>(target->lin); P.dst_f32 = nullptr;
+    P.dst_dtype = target->dtype; P.dst_padded = target->padded;
+    dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
+    SFB_LAUNCH_CHECK(ctx);
+    target->array_stale = true;                   // the cudaArray copy is old: sample through the linear mirror
     return SFB_OK;
 }
 

@@ -16,6 +16,7 @@ struct RenderParams {
     int ssaa, subsample, comps;
     double inv_Wr, inv_Hr;   // 1/Wr, 1/Hr
     unsigned char* dst;
+    int dst_dtype, dst_padded;   // format of `dst` for sfb_render_target (SFB_DTYPE_*, stored components)
     float* dst_f32;
     int fast;                // scene-specific fast path allowed (set by the launcher after checking formats)
 };
@@ -228,7 +229,9 @@ SFB_DEV vec4 scene_mandelbrot(const RenderParams& P, const Frag& f) {
     int quality = int(1000.0f*P.u.iQuality);
     int iter = 0;
     for (; iter < quality; iter++) {
-        if (length(z) > 3.0f) break;
+        // length(z) > 3.0 without the square root: sqrtf is correctly rounded and monotone, and the float
+        // after 9 already has a root that rounds above 3, so the two tests agree for every dot(z, z)
+        if (dot(z, z) > 9.0f) break;
         z = mk2(z.x*z.x - z.y*z.y, z.x*z.y + z.y*z.x) + c;
     }
     float t = powf(1.0f - float(iter)/float(quality), 20.0f);
@@ -273,6 +276,137 @@ SFB_DEV vec4 scene_raymarch(const RenderParams& P, const Frag& f) {
         if (walk < 0.001f || walk > 100.0f) break;
     }
     return mk4(mk3(1.0f - sqrtf(float(steps))*0.1f), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-program / multi-layer / temporal scenes of examples/basic/demo.py. The host renders
+// each layer l of a program's texture with iLayer = l and rolls temporal textures afterwards
+// (shader.py:398-405); samplers arrive in the order sfb_scene_info reports.
+
+// examples/basic/demo.py:74-79 (inline GLSL of MultiShader.child)
+template <bool HW>
+SFB_DEV vec4 scene_multishader_child(const RenderParams& P, const Frag& f) {
+    return mk4(0.0f, 1.0f - f.stuv.x, 0.0f, 1.0f);
+}
+
+// examples/basic/demo.py:83-89 (inline GLSL of MultiShader.shader) — samplers: child
+template <bool HW>
+SFB_DEV vec4 scene_multishader(const RenderParams& P, const Frag& f) {
+    vec3 rgb = mk3(f.stuv.x, 0.0f, 0.0f);
+    rgb = rgb + xyz(texture<HW>(P.tex[0], f.astuv));
+    return mk4(rgb, 1.0f);
+}
+
+// multipass.frag:11-26 — float loop counters in strict IEEE float32, like the blur of visualizer.frag
+template <bool HW>
+SFB_DEV vec4 multipass_blur(const DevSampler& image, vec2 stuv, float radius, int directions, int steps) {
+    vec4 color = mk4(0.0f);
+    float weights = 0.0f;
+    for (float direction = 0.0f; direction < TAU; direction += TAU/float(directions)) {
+        for (float walk = 1.0f/float(steps); walk < 1.0f; walk += 1.0f/float(steps)) {
+            const vec2 offset = ((mk2(cosf(direction), sinf(direction))*radius)*walk)/2000.0f;
+            const vec4 sample = texture<HW>(image, stuv + offset);
+            const float weight = 1.0f - length(offset)/radius;
+            color = color + sample*weight;
+            weights += weight;
+        }
+    }
+    return color/weights;
+}
+
+// examples/basic/shaders/multipass.frag:28-47 — samplers: background, iScreen0x0
+template <bool HW>
+SFB_DEV vec4 scene_multipass(const RenderParams& P, const Frag& f) {
+    vec4 c = mk4(0.0f);
+    if (P.u.iLayer == 0) {
+        c = stexture<HW>(P.tex[0], f.stuv);
+    } else if (P.u.iLayer == 1) {
+        c = texture<HW>(P.tex[1], f.astuv);
+        if (f.gluv.x < 0.0f) c.x = 1.0f - c.x;
+        else                 c = multipass_blur<HW>(P.tex[1], f.astuv, 5.0f, 8, 8);
+    }
+    c.w = 1.0f;
+    return c;
+}
+
+// examples/basic/shaders/motionblur.frag:1-18 — extra[0].x = iScreenTemporal;
+// samplers: background, iScreen0x0 ... iScreen{T-1}x0 (iScreenTexture(i, 0, uv), texture.py:363-367)
+template <bool HW>
+SFB_DEV vec4 scene_motionblur(const RenderParams& P, const Frag& f) {
+    const Camera cam = get_camera(P.u, f);
+    vec4 c = mk4(0.0f);
+    if (P.u.iLayer == 0) {
+        c = stexture<HW>(P.tex[0], cam.stuv);
+    } else if (P.u.iLayer == 1) {
+        const int T = min(int(P.u.extra[0][0]), SFB_MAX_SAMPLERS - 1);
+        vec4 color = mk4(0.0f);
+        for (int i = 0; i < T; i++) {
+            const float factor = smoothstep(1.0f, 0.0f, float(i)/float(T));
+            color = color + texture<HW>(P.tex[1 + i], f.astuv)*factor;
+        }
+        c = (2.0f*color)/float(T);
+    }
+    c.w = 1.0f;
+    return c;
+}
+
+// examples/basic/demo.py:120-125 (inline GLSL of Dynamics) — extra[0].x = iShaderDynamics; samplers: background
+template <bool HW>
+SFB_DEV vec4 scene_dynamics(const RenderParams& P, const Frag& f) {
+    const vec2 uv = zoom(f.stuv, 0.85f + 0.1f*P.u.extra[0][0], mk2(0.5f));
+    return stexture<HW>(P.tex[0], uv);
+}
+
+// examples/basic/demo.py:150-154 (inline GLSL of Audio) — extra[0].x = iAudioVolume
+template <bool HW>
+SFB_DEV vec4 scene_audio(const RenderParams& P, const Frag& f) {
+    return mk4(mk3(P.u.extra[0][0]), 1.0f);
+}
+
+// texelFetch(sampler, ivec2, 0).r: no filter, no wrap; outside the image GLSL 3.30 leaves the result
+// undefined — zeros here, like the oracle (robust-access behaviour)
+SFB_DEV float texel_fetch_r(const DevSampler& s, int ix, int iy) {
+    if (ix < 0 || iy < 0 || ix >= s.w || iy >= s.h) return 0.0f;
+    return texel_fetch(s, ix, iy).x;
+}
+
+// examples/basic/shaders/life/simulation.glsl:20-50 — extra[0].x = iLifePeriod, extra[1].xy = iLifeSize;
+// samplers: iLife1x0 (the previous state). Only .r is meaningful (the target has one component)
+template <bool HW>
+SFB_DEV vec4 scene_life_simulation(const RenderParams& P, const Frag& f) {
+    const int period = int(P.u.extra[0][0]);
+    if (period != 0 && (P.u.iFrame % period) != 0)
+        return mk4(texture<HW>(P.tex[0], f.astuv).x, 0.0f, 0.0f, 1.0f);
+    const int px = int(f.astuv.x*P.u.extra[1][0]), py = int(f.astuv.y*P.u.extra[1][1]);
+    int near = 0, current = 0;
+    for (int x = -1; x <= 1; x++)
+        for (int y = -1; y <= 1; y++) {
+            const int cell = texel_fetch_r(P.tex[0], px + x, py + y) > 0.5f ? 1 : 0;
+            if (x == 0 && y == 0) current = cell; else near += cell;
+        }
+    // alive[9] = {0,0,1,1,0,...}: two or three neighbours survive; dead[9] = {0,0,0,1,0,...}: three are born
+    const int next = (current == 1) ? ((near == 2 || near == 3) ? 1 : 0) : ((near == 3) ? 1 : 0);
+    return mk4(float(next), 0.0f, 0.0f, 1.0f);
+}
+
+// examples/basic/shaders/life/visuals.glsl:11-38 — samplers: iLife0x0 ... iLife4x0
+template <bool HW>
+SFB_DEV vec4 scene_life_visuals(const RenderParams& P, const Frag& f) {
+    const Camera cam = get_camera(P.u, f);
+    const vec3 C1 = mk3(0.01060815f, 0.01808215f, 0.10018654f), C2 = mk3(0.38092887f, 0.12061482f, 0.32506528f);
+    const vec3 C3 = mk3(0.79650140f, 0.10506637f, 0.31063031f), C4 = mk3(0.95922872f, 0.53307513f, 0.37488950f);
+    if (cam.out_of_bounds) return mk4(C1, 1.0f);
+    const vec2 uv = cam.stuv;
+    const float exponent = 1.3f;
+    const float area = 1.0f/(exponent + 1.0f);
+    float life = 0.0f;
+    life += stexture<HW>(P.tex[0], uv).x;
+    life += stexture<HW>(P.tex[1], uv).x*powf(0.8f, exponent);
+    life += stexture<HW>(P.tex[2], uv).x*powf(0.6f, exponent);
+    life += stexture<HW>(P.tex[3], uv).x*powf(0.4f, exponent);
+    life += stexture<HW>(P.tex[4], uv).x*powf(0.2f, exponent);
+    life /= (5.0f*area);
+    return mk4(palette(life, C1, C2, C3, C4), 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,6 +538,14 @@ SFB_DEV vec4 shade(const RenderParams& P, const Frag& f) {
     if constexpr (SCENE == SFB_SCENE_MANDELBROT) return scene_mandelbrot<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_TETRATION)  return scene_tetration<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_RAYMARCH)   return scene_raymarch<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_MULTISHADER_CHILD) return scene_multishader_child<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_MULTISHADER)       return scene_multishader<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_MULTIPASS)         return scene_multipass<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_MOTIONBLUR)        return scene_motionblur<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_DYNAMICS)          return scene_dynamics<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_AUDIO)             return scene_audio<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_LIFE_SIMULATION)   return scene_life_simulation<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_LIFE_VISUALS)      return scene_life_visuals<HW>(P, f);
     return mk4(0.0f);
 }
 

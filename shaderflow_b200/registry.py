@@ -5,7 +5,8 @@ time (csrc/scenes.cuh), so "compiling" a fragment means recognising it:
 
   1. a directive anywhere in the text:   // sfb200: scene=<name>
   2. the xxh64 of the comment- and whitespace-stripped source equals that of a reference shader this
-     backend transliterates (hashes computed from the reference tree at /root/reference, v0.11.3);
+     backend transliterates, or of a GLSL string written inline in the reference's examples/basic/demo.py
+     (hashes computed from the reference tree at /root/reference, v0.11.3);
   3. otherwise SFB_ENOTFOUND → RuntimeError naming the built-in scenes (the reference would fall back
      to missing.glsl, shader.py:323-340; silently rendering something else would be worse here).
 """
@@ -29,6 +30,14 @@ KNOWN_HASHES: dict[str, str] = {
     "475ec2955adf6026": "mandelbrot",  # examples/fractals/shaders/mandelbrot.frag
     "02f51dae03a8eb5f": "tetration",  # examples/fractals/shaders/tetration.frag
     "312906c609de3e00": "raymarch",  # examples/basic/shaders/raymarch.frag
+    "a010821ebfbcc39b": "multipass",  # examples/basic/shaders/multipass.frag
+    "b5b561df2a143db1": "motionblur",  # examples/basic/shaders/motionblur.frag
+    "98a643038dfef36d": "life_simulation",  # examples/basic/shaders/life/simulation.glsl
+    "9cbd4789b24a5591": "life_visuals",  # examples/basic/shaders/life/visuals.glsl
+    "afe91e9ac847e4bc": "multishader_child",  # examples/basic/demo.py:74 (MultiShader.child, inline)
+    "0bd0cc47bdf3fe09": "multishader",  # examples/basic/demo.py:83 (MultiShader.shader, inline)
+    "d6cf2b9635b9b18f": "dynamics",  # examples/basic/demo.py:120 (Dynamics.shader, inline)
+    "361c716bb6b8438f": "audio",  # examples/basic/demo.py:150 (Audio.shader, inline)
 }
 
 

@@ -125,7 +125,7 @@ class ShaderProgram(ShaderModule):
             return self
         name = registry.resolve(self._fragment)
         if name is None:
-            names = [N.scene_info(i)["name"] for i in range(8)]
+            names = [N.scene_info(i)["name"] for i in range(N.SCENE_COUNT)]
             raise RuntimeError(logger.error(
                 f"ShaderProgram '{self.name}': this fragment shader is not one the CUDA backend has a "
                 f"kernel for (digest {registry.digest(self.fragment)}). Built-in scenes: {names}. "
@@ -151,9 +151,12 @@ class ShaderProgram(ShaderModule):
 
     def resolve_samplers(self, samplers: dict[str, TextureBox]) -> list:
         out = []
-        for name in self.scene_info["samplers"]:
+        required = self.scene_info.get("required", len(self.scene_info["samplers"]))
+        for index, name in enumerate(self.scene_info["samplers"]):
             box = samplers.get(name)
             if box is None or box.texture is None:
+                if index >= required:
+                    break                      # the history of a temporal texture ends where the scene made it end
                 raise RuntimeError(f"Shader '{self.name}' samples '{name}' but the scene has no such texture")
             out.append(box.texture)
         return out
@@ -183,12 +186,12 @@ class ShaderProgram(ShaderModule):
             return
         values, samplers = self.gather(self.full_pipeline())
         textures = self.resolve_samplers(samplers)
-        w, h = self.texture.size
+        # one pass per layer into the newest temporal slot, then the history rolls (shader.py:398-405)
         for layer, box in enumerate(self.texture.row(0)):
             values["iLayer"] = layer
             block = self.uniform_block(values)
-            pointer, _ = box.texture.storage()
-            cuda.render_screen(self.scene_id, block, textures, w, h, pointer, None, self.filter_flags)
+            cuda.render_target(self.scene_id, block, textures, box.texture, self.filter_flags)
+            box.empty = False
         self.texture.roll()
 
     def render_fused(self, target: int, ssaa: int) -> None:

@@ -47,8 +47,10 @@ def native_uniforms(u: G.Uniforms, scene_info: dict):
                 "iCameraZoom", "iCameraIsometric", "iCameraFocalLength", "iCameraOrbital", "iCameraDolly", "iCameraSeparation"):
         setattr(n, key, float(getattr(u, key)))
     n.iFrame, n.iCameraMode, n.iCameraProjection = u.iFrame, u.iCameraMode, u.iCameraProjection
+    n.iLayer = int(getattr(u, "iLayer", 0))
     for key in ("iCameraPosition", "iCameraRight", "iCameraUpward", "iCameraForward", "iCameraZenith"):
         getattr(n, key)[:] = tuple(float(v) for v in getattr(u, key))
     for slot, name in enumerate(scene_info["extra"]):
-        n.extra[slot][0] = float(u.extra[name])
+        for k, value in enumerate(np.asarray(u.extra[name], dtype=np.float64).reshape(-1)[:4]):
+            n.extra[slot][k] = float(value)
     return n

@@ -130,7 +130,7 @@ def test_registry_directive_and_normalisation():
     b = "/* header */ void main(){fragColor=vec4(1.0);}"
     assert registry.digest(a) == registry.digest(b)
     assert registry.resolve(a) is None
-    assert len(registry.KNOWN_HASHES) == 8
+    assert len(registry.KNOWN_HASHES) == 16 and len(set(registry.KNOWN_HASHES.values())) == 16
 
 
 @pytest.mark.reference
@@ -141,8 +141,21 @@ def test_registry_hashes_match_reference_tree():
         pytest.skip("no /root/reference here")
     for rel, name in (("examples/basic/shaders/visualizer.frag", "visualizer"), ("examples/basic/shaders/bars.frag", "bars"),
                       ("examples/fractals/shaders/mandelbrot.frag", "mandelbrot"),
-                      ("shaderflow/resources/shaders/fragment/default.glsl", "default")):
+                      ("shaderflow/resources/shaders/fragment/default.glsl", "default"),
+                      ("examples/basic/shaders/multipass.frag", "multipass"), ("examples/basic/shaders/motionblur.frag", "motionblur"),
+                      ("examples/basic/shaders/life/simulation.glsl", "life_simulation"),
+                      ("examples/basic/shaders/life/visuals.glsl", "life_visuals")):
         assert registry.resolve(ref/rel) == name
+    # the GLSL written inline in the reference's demo.py is recognised as the text the user scene passes
+    import ast
+    inline = {}
+    for cls in (n for n in ast.parse((ref/"examples/basic/demo.py").read_text()).body if isinstance(n, ast.ClassDef)):
+        for node in ast.walk(cls):
+            if isinstance(node, ast.Assign) and isinstance(node.value, ast.Constant) and isinstance(node.value.value, str) \
+                    and isinstance(node.targets[0], ast.Attribute) and node.targets[0].attr == "fragment":
+                inline[(cls.name, node.targets[0].value.attr)] = registry.resolve(node.value.value)
+    assert inline == {("MultiShader", "child"): "multishader_child", ("MultiShader", "shader"): "multishader",
+                      ("Dynamics", "shader"): "dynamics", ("Audio", "shader"): "audio"}
 
 
 def test_host_dynamics_matches_reference_golden(golden_dir):
