@@ -175,6 +175,30 @@ class Visualizer(ShaderScene):
             self.back.from_image(message.first)
 
 
+class PianoRoll(ShaderScene):
+    """Piano roll: ShaderPiano + examples/shaders/piano.frag (BASELINE config 5's scene; the reference ships the
+    module but neither a scene nor a fragment for it). Notes come from `notes` rows (pitch, start, end, channel,
+    velocity) or a seeded synthetic list: 4 channels, 16 notes/s, pitches 36-96, 0.1-1 s."""
+    notes = None
+    seconds: float = 10.0
+
+    def build(self):
+        from shaderflow.piano import PianoNote, ShaderPiano
+        self.piano = ShaderPiano(scene=self)
+        for (pitch, start, end, channel, velocity) in (self.notes if self.notes is not None else synthetic_notes(self.seconds)):
+            self.piano.add_note(PianoNote(note=int(pitch), start=float(start), end=float(end), channel=int(channel), velocity=int(velocity)))
+        self.shader.fragment = (shaders/"piano.frag")
+
+
+def synthetic_notes(seconds: float, seed: int = 5, channels: int = 4, rate: float = 16.0) -> list:
+    rng = np.random.default_rng(seed)
+    notes = []
+    for channel in range(channels):
+        for s in np.sort(rng.uniform(-0.5, seconds, int(seconds*rate/channels))):
+            notes.append((int(rng.integers(36, 97)), float(s), float(s + rng.uniform(0.1, 1.0)), channel, int(rng.integers(20, 128))))
+    return notes
+
+
 class RayMarch(ShaderScene):
     """Ray Marching demo"""
     def build(self):

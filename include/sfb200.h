@@ -120,6 +120,37 @@ int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_samples, int c
                     double* scalars_out_dev,
                     float* wave_out_dev, int wave_points, int wave_chunk, int wave_reducer);
 
+/* DynamicNumber.next (dynamics.py:197-250) over frames for any float32 vector, in place on
+ * values_inout_dev [n_frames][lanes]: row k holds the target of frame k on entry and the state after frame
+ * k's update on return. Same kernel as the spectrogram columns of sfb_audio_track. */
+int sfb_dynamics_scan(sfb_ctx* ctx, float* values_inout_dev, int lanes, const double* dt_dev, int n_frames,
+                      const sfb_dynamics_params* params);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Piano roll — replaces the per-frame Python tree walk of ShaderPiano.update (piano/module.py:202-277).
+ * notes_dev: every note of the scene, sorted by pitch (stable in insertion order); pitch_offset_dev [129]:
+ * notes of pitch p are notes_dev[pitch_offset[p] .. pitch_offset[p+1]). `order` is the insertion index
+ * (add_note call order), which together with the integer-second bucket decides the reference's iteration
+ * order, hence the roll slots and which note wins a key. */
+typedef struct sfb_piano_note {
+    double start, end;          /* seconds, float64 like PianoNote.start/.end */
+    int32_t note, channel, velocity, order;
+} sfb_piano_note;
+
+/* All frames at once: for frame k at scene time time_dev[k] writes the key-press targets and the channel row
+ * update() would build (module.py:213-247; channel -1 = not playing) and the lowest / highest pitch with
+ * upcoming notes (module.py:262-266; (128, -1) when there is none). [n_frames][128], [n_frames][128], [n_frames][2] */
+int sfb_piano_track(sfb_ctx* ctx, const sfb_piano_note* notes_dev, const int32_t* pitch_offset_dev,
+                    const double* time_dev, int n_frames, double time_offset, double roll_time,
+                    double lookup_time, double release_before_end, int global_min, int global_max,
+                    float* key_target_out_dev, float* channel_out_dev, int32_t* upcoming_out_dev);
+/* One frame's roll texture (module.py:222-231) into roll_out_dev [128][256][4] float32 — e.g. the storage of
+ * the iPianoRoll texture: texel (slot, pitch) = (start, end, channel, velocity). *overflow_dev is set to 1 when a
+ * pitch has more than 2048 visited notes in the window (slots would then be wrong). */
+int sfb_piano_roll(sfb_ctx* ctx, const sfb_piano_note* notes_dev, const int32_t* pitch_offset_dev,
+                   double time, double roll_time, double lookup_time, int global_min, int global_max,
+                   float* roll_out_dev, int32_t* overflow_dev);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* Textures — replaces moderngl Context.texture / Texture.write / .filter / .repeat_x/y as used by
  * ShaderTexture.make/apply/write (texture.py:250-283,313-325). Backed by a cudaArray + texture object
@@ -168,7 +199,9 @@ enum {
     SFB_SCENE_AUDIO = 13,             /* examples/basic/demo.py:150-154, inline    (Audio)              */
     SFB_SCENE_LIFE_SIMULATION = 14,   /* examples/basic/shaders/life/simulation.glsl (Life.simulation)  */
     SFB_SCENE_LIFE_VISUALS = 15,      /* examples/basic/shaders/life/visuals.glsl  (Life)               */
-    SFB_SCENE_COUNT = 16,
+    SFB_SCENE_PIANO = 16,             /* examples/shaders/piano.frag of THIS repository (the reference ships  */
+                                      /* ShaderPiano but no fragment for it)                                 */
+    SFB_SCENE_COUNT = 17,
 };
 
 #define SFB_MAX_EXTRA 16

@@ -22,7 +22,7 @@ DTYPE_U8, DTYPE_F32, DTYPE_F16 = 0, 1, 2
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
 FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL, RENDER_TILED = 0, 1, 2, 4
 SCALARS = 5
-SCENE_COUNT = 16
+SCENE_COUNT = 17
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
 
 
@@ -58,6 +58,12 @@ class Uniforms(C.Structure):
 
 class DynamicsParams(C.Structure):
     _fields_ = [("frequency", c_double), ("zeta", c_double), ("response", c_double), ("precision", c_double)]
+
+
+class PianoNote(C.Structure):
+    """struct sfb_piano_note"""
+    _fields_ = [("start", c_double), ("end", c_double), ("note", c_int32), ("channel", c_int32),
+                ("velocity", c_int32), ("order", c_int32)]
 
 
 class SceneInfo(C.Structure):
@@ -96,6 +102,10 @@ _PROTOTYPES = dict(
     sfb_scene_info_get=(c_int, [c_int, POINTER(SceneInfo)]),
     sfb_render_screen=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
                                c_int, c_int, c_void_p, c_void_p]),
+    sfb_dynamics_scan=(c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(DynamicsParams)]),
+    sfb_piano_track=(c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
+                             c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    sfb_piano_roll=(c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     sfb_render_target=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int, c_void_p]),
     sfb_render_final=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_render_frame=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
@@ -317,6 +327,21 @@ class Context:
         prm = DynamicsParams(*dynamics)
         check(lib().sfb_audio_track(self.handle, _ptr(pcm), n, channels, samplerate, _ptr(tell), _ptr(dt), tell.shape[0],
             _ptr(spec), bins, byref(prm), _ptr(scalars), _ptr(wave), wave_points, wave_chunk, wave_reducer))
+
+    def dynamics_scan(self, values, lanes: int, dt, n_frames: int, dynamics: tuple[float, float, float, float]) -> None:
+        """DynamicNumber.next over frames, in place on values [n_frames, lanes] float32 cuda"""
+        prm = DynamicsParams(*dynamics)
+        check(lib().sfb_dynamics_scan(self.handle, _ptr(values), lanes, _ptr(dt), n_frames, byref(prm)))
+
+    def piano_track(self, notes, offsets, time, n_frames: int, time_offset: float, roll_time: float, lookup_time: float,
+                    release: float, gmin: int, gmax: int, keys, channel, upcoming) -> None:
+        check(lib().sfb_piano_track(self.handle, _ptr(notes), _ptr(offsets), _ptr(time), n_frames, time_offset, roll_time,
+                                    lookup_time, release, gmin, gmax, _ptr(keys), _ptr(channel), _ptr(upcoming)))
+
+    def piano_roll(self, notes, offsets, time: float, roll_time: float, lookup_time: float, gmin: int, gmax: int,
+                   roll, overflow) -> None:
+        check(lib().sfb_piano_roll(self.handle, _ptr(notes), _ptr(offsets), time, roll_time, lookup_time, gmin, gmax,
+                                   _ptr(roll), _ptr(overflow)))
 
     # -- render ----------------------------------------------------------------------------- #
 

@@ -618,3 +618,15 @@ extern "C" int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_sam
     }
     return SFB_OK;
 }
+
+// DynamicNumber.next over frames for any float32 vector (ShaderPiano's key presses, piano/module.py:63-67,268):
+// the same sequential scan as the spectrogram columns, in place on values_inout_dev [n_frames][lanes]
+extern "C" int sfb_dynamics_scan(sfb_ctx* ctx, float* values_inout_dev, int lanes, const double* dt_dev, int n_frames,
+                                 const sfb_dynamics_params* params) {
+    SFB_REQUIRE(ctx && values_inout_dev && dt_dev && params, "sfb_dynamics_scan: null argument");
+    SFB_REQUIRE(n_frames > 0 && lanes > 0 && lanes <= SCAN_THREADS*SCAN_ELEMS,
+        "sfb_dynamics_scan: lanes = %d outside 1..%d", lanes, SCAN_THREADS*SCAN_ELEMS);
+    spec_scan_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(values_inout_dev, lanes, dt_dev, n_frames, *params);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}

@@ -192,6 +192,9 @@ static const sfb_scene_info SCENES[SFB_SCENE_COUNT] = {
     {"life_simulation", "examples/basic/shaders/life/simulation.glsl", 2, {"iLifePeriod", "iLifeSize"}, 1, {"iLife1x0"}, 1},
     {"life_visuals", "examples/basic/shaders/life/visuals.glsl", 0, {},
                    5, {"iLife0x0", "iLife1x0", "iLife2x0", "iLife3x0", "iLife4x0"}, 5},
+    {"piano",      "examples/shaders/piano.frag (this repository)", 6,
+                   {"iPianoDynamic", "iPianoExtra", "iPianoHeight", "iPianoBlackRatio", "iPianoRollTime", "iPianoLimit"},
+                   3, {"iPianoKeys", "iPianoChan", "iPianoRoll"}, 3},
 };
 
 extern "C" int sfb_scene_lookup(const char* name, int* scene) {
@@ -271,7 +274,7 @@ static void dispatch(int scene, bool hw, A... a) {
         SFB_CASE(SFB_SCENE_TETRATION) SFB_CASE(SFB_SCENE_RAYMARCH)
         SFB_CASE(SFB_SCENE_MULTISHADER_CHILD) SFB_CASE(SFB_SCENE_MULTISHADER) SFB_CASE(SFB_SCENE_MULTIPASS)
         SFB_CASE(SFB_SCENE_MOTIONBLUR) SFB_CASE(SFB_SCENE_DYNAMICS) SFB_CASE(SFB_SCENE_AUDIO)
-        SFB_CASE(SFB_SCENE_LIFE_SIMULATION) SFB_CASE(SFB_SCENE_LIFE_VISUALS)
+        SFB_CASE(SFB_SCENE_LIFE_SIMULATION) SFB_CASE(SFB_SCENE_LIFE_VISUALS) SFB_CASE(SFB_SCENE_PIANO)
     }
     #undef SFB_CASE
 }

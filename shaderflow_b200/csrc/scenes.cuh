@@ -409,6 +409,54 @@ SFB_DEV vec4 scene_life_visuals(const RenderParams& P, const Frag& f) {
     return mk4(palette(life, C1, C2, C3, C4), 1.0f);
 }
 
+// texelFetch(sampler, ivec2, 0): all four components (zeros outside, like texel_fetch_r)
+SFB_DEV vec4 texel_fetch_raw(const DevSampler& s, int ix, int iy) {
+    if (ix < 0 || iy < 0 || ix >= s.w || iy >= s.h) return mk4(0.0f);
+    return texel_fetch(s, ix, iy);
+}
+
+// examples/shaders/piano.frag of this repository (the reference ships ShaderPiano, piano/module.py, without a
+// fragment). extra: iPianoDynamic (vec2), iPianoExtra, iPianoHeight, iPianoBlackRatio, iPianoRollTime,
+// iPianoLimit; samplers: iPianoKeys, iPianoChan, iPianoRoll
+SFB_DEV vec3 piano_channel_color(float channel) { return hsv2rgb(0.6f + 0.9f*channel, 0.75f, 1.0f); }
+
+template <bool HW>
+SFB_DEV vec4 scene_piano(const RenderParams& P, const Frag& f) {
+    const float dyn_lo = P.u.extra[0][0], dyn_hi = P.u.extra[0][1], extra = P.u.extra[1][0];
+    const float height = P.u.extra[2][0], black_ratio = P.u.extra[3][0], roll_time = P.u.extra[4][0];
+    const int limit = int(P.u.extra[5][0]);
+    vec3 rgb = mk3(0.06f);
+    const float lo = dyn_lo - extra, hi = dyn_hi + extra + 1.0f;
+    const float keyf = mix(lo, hi, f.astuv.x);
+    const float keyi = floorf(keyf);
+    const float inkey = keyf - keyi;
+    if ((keyi < 0.0f) || (keyi > 127.0f)) return mk4(rgb, 1.0f);
+    const int key = int(keyi);
+    const int k12 = key - 12*(key/12);
+    const bool black = (k12 == 1) || (k12 == 3) || (k12 == 6) || (k12 == 8) || (k12 == 10);
+    if (f.astuv.y < height) {
+        const float press = clamp(texel_fetch_raw(P.tex[0], key, 0).x/128.0f, 0.0f, 1.0f);
+        const float chan = texel_fetch_raw(P.tex[1], key, 0).x;
+        vec3 base = black ? mk3(0.12f) : mk3(0.92f);
+        if (black && (f.astuv.y < height*(1.0f - black_ratio))) base = mk3(0.92f);
+        rgb = base;
+        if (chan >= 0.0f) rgb = mix(base, piano_channel_color(chan), press);
+        if (inkey < 0.06f) rgb = rgb*0.55f;
+    } else {
+        const float when = P.u.iTime + roll_time*(f.astuv.y - height)/(1.0f - height);
+        rgb = black ? mk3(0.09f) : mk3(0.12f);
+        for (int i = 0; i < limit; i++) {
+            const vec4 note = texel_fetch_raw(P.tex[2], i, key);
+            if (note.x == 0.0f && note.y == 0.0f && note.z == 0.0f && note.w == 0.0f) break;
+            if ((note.x <= when) && (when <= note.y)) {
+                rgb = piano_channel_color(note.z)*(0.35f + 0.65f*note.w/128.0f);
+                if ((inkey < 0.08f) || (inkey > 0.92f)) rgb = rgb*0.5f;
+            }
+        }
+    }
+    return mk4(rgb, 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // visualizer.frag, production path. Same mathematics as scene_visualizer (the literal transliteration
 // above stays as the parity anchor and serves SFB_FILTER_HARDWARE / unusual texture formats); what
@@ -546,6 +594,7 @@ SFB_DEV vec4 shade(const RenderParams& P, const Frag& f) {
     if constexpr (SCENE == SFB_SCENE_AUDIO)             return scene_audio<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_LIFE_SIMULATION)   return scene_life_simulation<HW>(P, f);
     if constexpr (SCENE == SFB_SCENE_LIFE_VISUALS)      return scene_life_visuals<HW>(P, f);
+    if constexpr (SCENE == SFB_SCENE_PIANO)             return scene_piano<HW>(P, f);
     return mk4(0.0f);
 }
 
