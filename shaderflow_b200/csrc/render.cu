@@ -334,6 +334,21 @@ template <int S> static cudaError_t launch_visualizer_tiled(const VisualizerPara
     return cudaSuccess;
 }
 
+// The iScreen pass of an unfused visualizer export (the reference's default ssaa=1, subsample=2 blends
+// neighbours in final.glsl, so K3 and K4 stay separate): the tiled kernel with one fragment per thread and an
+// RGBA8 store that keeps fragColor.a
+static int visualizer_screen_pass(sfb_ctx* ctx, const RenderParams& P, sfb_tex* background) {
+    VisualizerParams VP;
+    VP.R = P;
+    VP.R.W = P.Wr; VP.R.H = P.Hr; VP.R.ssaa = 1; VP.R.subsample = 1; VP.R.comps = 4;
+    VP.tmap = background_tensor_map(background);
+    VP.use_tma = VP.tmap ? 1 : 0;
+    VP.screen_alpha = 1;
+    SFB_CUDA(launch_visualizer_tiled<1>(VP, ctx->stream));
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
 extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
                                  sfb_tex* const* samplers, int n_samplers, int flags,
                                  int target_w, int target_h, void* dst_rgba8_dev, float* dst_f32_dev) {
@@ -346,6 +361,8 @@ extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.inv_Wr = 1.0/double(target_w); P.inv_Hr = 1.0/double(target_h);
     P.dst = static_cast<unsigned char*>(dst_rgba8_dev); P.dst_f32 = dst_f32_dev;
     P.dst_dtype = SFB_DTYPE_U8; P.dst_padded = 4;
+    if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && !dst_f32_dev)
+        return visualizer_screen_pass(ctx, P, samplers[0]);
     dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
@@ -364,9 +381,11 @@ extern "C" int sfb_render_target(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
     P.dst = static_cast<unsigned char*>(target->lin); P.dst_f32 = nullptr;
     P.dst_dtype = target->dtype; P.dst_padded = target->padded;
+    target->array_stale = true;                   // the cudaArray copy is old: sample through the linear mirror
+    if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && target->dtype == SFB_DTYPE_U8 && target->padded == 4)
+        return visualizer_screen_pass(ctx, P, samplers[0]);
     dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
-    target->array_stale = true;                   // the cudaArray copy is old: sample through the linear mirror
     return SFB_OK;
 }
 
@@ -412,6 +431,7 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
         VP.R = P;
         VP.tmap = background_tensor_map(samplers[0]);
         VP.use_tma = VP.tmap ? 1 : 0;
+        VP.screen_alpha = 0;
         cudaError_t e;
         switch (ssaa) {
             case 1: e = launch_visualizer_tiled<1>(VP, ctx->stream); break;

@@ -41,6 +41,7 @@ struct VisualizerParams {
     RenderParams R;
     const CUtensorMap* tmap;                           // device copy of the 2D uint32 view of the background's linear mirror
     int use_tma;
+    int screen_alpha;                                  // iScreen pass (sfb_render_screen): store fragColor.a, not 255
 };
 
 // --- mbarrier / TMA helpers (inline PTX, sm_90+) ---------------------------------------------------
@@ -224,7 +225,7 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
     __syncthreads();
 
     // ---- C + D. shade ----------------------------------------------------------------------------
-    unsigned int r8 = 0, g8 = 0, b8 = 0;
+    unsigned int r8 = 0, g8 = 0, b8 = 0, a8 = 0;
     if (inside) {
         #pragma unroll
         for (int s = 0; s < S*S; s++) {
@@ -275,14 +276,16 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
             r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
             g8 += (unsigned int)__float2int_rn(__saturatef(c.y)*255.0f);
             b8 += (unsigned int)__float2int_rn(__saturatef(c.z)*255.0f);
+            a8 += (unsigned int)__float2int_rn(__saturatef(c.w)*255.0f);
         }
         const float inv = 1.0f/float(S*S);
+        a8 = VP.screen_alpha ? (unsigned int)__float2int_rn(float(a8)*inv) : 255u;
         r8 = (unsigned int)__float2int_rn(float(r8)*inv);
         g8 = (unsigned int)__float2int_rn(float(g8)*inv);
         b8 = (unsigned int)__float2int_rn(float(b8)*inv);
     }
     if (P.comps == 4) {
-        if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
+        if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, a8);
         return;
     }
     const bool words = (P.W % 4 == 0) && (blockIdx.x*VT_TILE_X + VT_TILE_X <= P.W);

@@ -286,3 +286,26 @@ def test_separable_visualizer_kernel_equals_tiled_and_oracle(ctx, bg_size, out, 
         ref = G.render("visualizer", u, tex, Wo, Ho, ssaa=float(ssaa), subsample=ssaa)
         d = np.abs(rows.astype(int) - ref["final_u8"].astype(int))
         assert (d <= 1).mean() >= 0.999, (d <= 1).mean()
+
+
+@pytest.mark.parametrize("want_aspect", [None, 1.25])
+def test_visualizer_screen_pass_into_rgba8_target(ctx, scene_inputs, want_aspect):
+    """The iScreen pass of an unfused export (sfb_render_target into an RGBA8 texture) runs the tiled kernel with one
+    fragment per thread: same bytes as the generic per-fragment pass, alpha included (0 where the fragment is out of
+    bounds: a wanted aspect narrower than the target's leaves bars on both sides, camera.glsl:86)"""
+    from shaderflow_b200 import _native as N
+    tex, extra, time = scene_inputs
+    u = uniforms_for("visualizer", extra, time)
+    camera = want_aspect is not None
+    if camera:
+        u.iWantAspect = want_aspect
+    rgba, _, (sid, info, samplers, _) = gpu_screen(ctx, "visualizer", u, tex, W, H)
+    target = N.Texture(ctx, W, H, 4, N.DTYPE_U8)
+    ctx.render_target(sid, native_uniforms(u, info), samplers, target)
+    ctx.sync()
+    got = target.read()
+    d = np.abs(got.astype(int) - rgba.astype(int))
+    assert (d <= 1).mean() > 0.9999 and (d == 0).mean() > 0.995, ((d <= 1).mean(), (d == 0).mean())
+    assert np.array_equal(got[..., 3], rgba[..., 3])
+    if camera:
+        assert (got[..., 3] == 0).any() and (got[..., 3] == 255).any()
