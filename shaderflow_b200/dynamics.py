@@ -9,7 +9,7 @@ from __future__ import annotations
 import math
 from copy import deepcopy
 from numbers import Number
-from typing import Iterable, Optional
+from typing import Any, Iterable, Optional
 
 import numpy as np
 from attrs import define, field
@@ -78,6 +78,7 @@ class DynamicNumber(_Arithmetic):
     derivative: np.ndarray = 0.0
     acceleration: np.ndarray = 0.0
     previous: np.ndarray = 0.0
+    _at_rest: Any = None
 
     def __attrs_post_init__(self):
         self.set(self.target or self.value)
@@ -121,10 +122,20 @@ class DynamicNumber(_Arithmetic):
             self.target = self._ensure_numpy(target)
             if self.target.shape != self.value.shape:
                 self.set(target)
+        # A system that was at rest last time and whose target and value still hold the same bytes (in-place edits
+        # of either are seen) is at rest again: every export steps ~10 such systems per frame, and a sharded rank
+        # steps them through all the frames before its range
+        key = None
+        if not self.integrate:
+            key = (self.target.tobytes(), self.value.tobytes())
+            if key == self._at_rest:
+                return self.value
         if _max_abs_difference(self.target, self.value) < self.precision:
             if self.integrate:
                 self.integral += self.value*dt
+            self._at_rest = key
             return self.value
+        self._at_rest = None
         velocity = (self.target - self.previous)/dt
         self.previous = self.target
         if self.radians*dt < self.zeta:        # clamp k2 to stable values
