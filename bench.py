@@ -347,7 +347,8 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, ms_each_step=[round(float(m), 2) for m in value_ms], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=WORKLOAD, frames_per_step_per_gpu=F, global_frames_per_step=total_frames,
-                            parallelism=f"frame-shard x{world} + gather to rank 0" if world > 1 else "single GPU",
+                            parallelism=(f"frame-shard x{world}: contiguous ranges, ranks shade straight into rank 0's HBM over NVLink "
+                                         "(CUDA IPC peer writes), NCCL barrier, rank 0 feeds the sink") if world > 1 else "single GPU",
                             filter="hardware" if args.hardware_filter else "exact",
                             l2="each step streams %.2f GB of frames per GPU (>> 126 MB L2); the 8.3 MB background is reused "
                                "across frames by design" % (F*W*H*3/1e9)),
