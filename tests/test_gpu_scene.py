@@ -132,3 +132,20 @@ def test_unknown_glsl_is_an_error_and_hash_lookup_works():
         scene.main(width=64, height=36, time=0.1)
     assert {"default", "shadertoy", "visualizer", "bars", "waveform", "mandelbrot", "tetration", "raymarch",
             "multipass", "motionblur", "life_simulation", "life_visuals"} <= set(registry.KNOWN_HASHES.values())
+
+
+def test_sharded_export_equals_single_gpu_export():
+    """Frame-sharded export over 2 GPUs (peer writes into rank 0's HBM, or the NCCL fallback) must produce exactly the
+    bytes of the single-GPU export — tools/shard_check.py under torchrun. Needs two visible GPUs."""
+    import subprocess, sys
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    for env_extra in ({}, {"SFB_NO_PEER_FRAMES": "1"}):
+        import os
+        done = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                               "--master-port", "29541", str(root/"tools"/"shard_check.py")], capture_output=True, text=True, timeout=600,
+                              env={**os.environ, **env_extra})
+        assert done.returncode == 0 and "-> OK" in done.stdout, (env_extra, done.stdout[-2000:], done.stderr[-2000:])
