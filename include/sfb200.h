@@ -273,6 +273,13 @@ int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
                      sfb_tex* const* samplers, int n_samplers, int flags,
                      int width, int height, int ssaa, int subsample, int components, void* dst_dev);
 
+/* Which kernel sfb_render_frame picks for the visualizer scene (no GPU needed; diagnostics and tests):
+ * *rows_per_thread = 8 or 4 when the separable kernel (one thread per fragment column) shades the frame and
+ * *window_rows = background rows it stages per CTA; 0 when the per-pixel tiled kernel does (rotated / stereo /
+ * equirectangular camera, ssaa 3, or a vertical texel step per fragment too coarse for 4 texel rows). */
+int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int background_h,
+                        int width, int height, int ssaa, int* rows_per_thread, int* window_rows);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* Frame sink — replaces turbopipe.pipe/sync/done + fbo.read_into (exporting.py:140-174): a ring of
  * n_buffers device frames, each paired with a pinned host buffer; submit enqueues an async D2H on a copy

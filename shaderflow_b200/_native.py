@@ -106,6 +106,7 @@ _PROTOTYPES = dict(
     sfb_piano_track=(c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
                              c_int, c_int, c_void_p, c_void_p, c_void_p]),
     sfb_piano_roll=(c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
+    sfb_visualizer_plan=(c_int, [POINTER(Uniforms), c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     sfb_render_target=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int, c_void_p]),
     sfb_render_final=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_render_frame=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
@@ -181,6 +182,13 @@ def scene_lookup(name: str) -> int:
     scene = c_int(-1)
     check(lib().sfb_scene_lookup(name.encode(), byref(scene)))
     return scene.value
+
+
+def visualizer_plan(uniforms: Uniforms, background: tuple[int, int], width: int, height: int, ssaa: int) -> tuple[int, int]:
+    """(fragment rows per thread of the separable kernel or 0 = tiled kernel, window rows); host-only"""
+    rows, window = c_int(), c_int()
+    check(lib().sfb_visualizer_plan(byref(uniforms), background[0], background[1], width, height, ssaa, byref(rows), byref(window)))
+    return rows.value, window.value
 
 
 def scene_info(scene: int) -> dict:

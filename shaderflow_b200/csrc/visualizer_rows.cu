@@ -38,6 +38,7 @@
 #include "visualizer_rows.h"
 
 #include <math.h>
+#include <atomic>
 
 namespace glsl {
 
@@ -541,6 +542,8 @@ static int build_rows_tables() {
     return SFB_OK;
 }
 
+static std::atomic<unsigned int> g_next_slot{0};
+
 template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
     static bool configured = false;
     const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
@@ -554,9 +557,8 @@ template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaSt
     size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
     if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
-    // frame constants first (same stream): consecutive frames rotate through the slots
-    static unsigned int next_slot = 0;
-    VP.slot = int(next_slot++ % VR_SLOTS);
+    // frame constants first (same stream): consecutive launches of the process rotate through the slots
+    VP.slot = int(g_next_slot.fetch_add(1u) % VR_SLOTS);
     const sfb_uniforms& u = VP.R.u;
     visualizer_frame_consts_kernel<<<1, 32, 0, st>>>(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h), VP.slot);
     visualizer_rows_kernel<S, J><<<grid, block, smem, st>>>(VP);
@@ -564,18 +566,19 @@ template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaSt
 }
 
 // Launch planning on the host: the same vis_front the kernel evaluates gives the texel step per fragment.
-int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched) {
-    *launched = 0;
-    static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
-    if (disabled) return SFB_OK;
+// Launch planning, pure host code: which variant (J fragment rows per thread) shades this frame and how many
+// window rows it stages; J = 0 when the frame does not qualify (the tiled kernel takes it). The same vis_front
+// the kernel evaluates gives the texel step per fragment.
+static void plan_rows(const RenderParams& P, int* J_out, int* win_h_out) {
+    *J_out = 0; *win_h_out = 0;
     const sfb_uniforms& u = P.u;
     const int S = P.ssaa;
-    if (!(S == 1 || S == 2 || S == 4)) return SFB_OK;
+    if (!(S == 1 || S == 2 || S == 4)) return;
     // separable camera: 2D ray through the z = 1 plane with the canonical basis (camera.glsl:55-91)
     const bool canonical = u.iCameraProjection == 0
         && u.iCameraRight[0] == 1.0f && u.iCameraRight[1] == 0.0f && u.iCameraRight[2] == 0.0f
         && u.iCameraUpward[0] == 0.0f && u.iCameraUpward[1] == 1.0f && u.iCameraUpward[2] == 0.0f;
-    if (!canonical || P.Wr < 2 || P.Hr < 2) return SFB_OK;
+    if (!canonical || P.Wr < 2 || P.Hr < 2) return;
     const DevSampler& bg = P.tex[0];
     const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
     const float iTime = u.iTime, vol = u.extra[0][0];
@@ -587,16 +590,40 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* 
     const vec2 t01 = vis_front(P, 0, P.Hr - 1, fw, fh, hw, wobble, zf).tap;
     const double sx = fabs(double(t10.x) - double(t00.x))/double(P.Wr - 1);
     const double sy = fabs(double(t01.y) - double(t00.y))/double(P.Hr - 1);
-    if (!(sx == sx && sy == sy && scale == scale) || !(sx < 1e6 && sy < 1e6 && scale < 1e6)) return SFB_OK;
-    if (t10.y != t00.y || t01.x != t00.x) return SFB_OK;               // not separable after all
+    if (!(sx == sx && sy == sy && scale == scale) || !(sx < 1e6 && sy < 1e6 && scale < 1e6)) return;
+    if (t10.y != t00.y || t01.x != t00.x) return;                      // not separable after all
     int J;
     if (7.0*sy <= 1.9 && 8 % S == 0) J = 8;
     else if (3.0*sy <= 1.9 && 4 % S == 0) J = 4;
-    else return SFB_OK;
+    else return;
     const double reach = double(scale)*1.0001 + 1.0;
-    if ((VR_COLS - 1)*sx + 2.0*reach + 9.0 > double(VR_WIN_W - 1)) return SFB_OK;
+    if ((VR_COLS - 1)*sx + 2.0*reach + 9.0 > double(VR_WIN_W - 1)) return;
     const int win_h = int(ceil((VR_GROUPS*J - 1)*sy + 2.0*reach)) + 11;   // + alignment, neighbours, the last row quad
-    if (win_h > VR_MAX_H) return SFB_OK;
+    if (win_h > VR_MAX_H) return;
+    *J_out = J; *win_h_out = win_h;
+}
+
+extern "C" int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int background_h,
+                                   int width, int height, int ssaa, int* rows_per_thread, int* window_rows) {
+    SFB_REQUIRE(uniforms && rows_per_thread && window_rows, "sfb_visualizer_plan: null argument");
+    SFB_REQUIRE(background_w > 0 && background_h > 0 && width > 0 && height > 0 && ssaa >= 1, "sfb_visualizer_plan: bad size");
+    RenderParams P{};
+    P.u = *uniforms;
+    P.tex[0].w = background_w; P.tex[0].h = background_h;
+    P.W = width; P.H = height; P.ssaa = ssaa; P.Wr = width*ssaa; P.Hr = height*ssaa;
+    P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
+    plan_rows(P, rows_per_thread, window_rows);
+    return SFB_OK;
+}
+
+int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched) {
+    *launched = 0;
+    static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
+    if (disabled) return SFB_OK;
+    int J = 0, win_h = 0;
+    plan_rows(P, &J, &win_h);
+    if (J == 0) return SFB_OK;
+    const int S = P.ssaa;
     if (int e = build_rows_tables()) return e;
     VisRowsParams VP;
     VP.R = P; VP.win_h = win_h;

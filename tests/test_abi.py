@@ -81,3 +81,20 @@ def test_argument_validation_without_gpu():
     assert lib.sfb_render_final(None, None, 0, 0, 0, 0, 0, 0, None) == N.EINVAL
     assert lib.sfb_frame_clock(-1, 60.0, 1.0, 44100, 2, -1, None, None, None) == N.EINVAL
     assert lib.sfb_scene_info_get(99, ctypes.byref(N.SceneInfo())) == N.EINVAL
+
+
+def test_visualizer_launch_plan_is_host_only():
+    """sfb_visualizer_plan needs no GPU: which kernel sfb_render_frame picks for the headline scene"""
+    from shaderflow_b200 import _native as N
+    u = N.Uniforms.defaults(3840, 2160); u.iTime = 1.0; u.extra[0][0] = 0.8
+    rows, window = N.visualizer_plan(u, (1920, 1080), 3840, 2160, 2)           # BASELINE configs[2]
+    assert rows == 8 and 20 <= window <= 40
+    assert N.visualizer_plan(u, (3840, 2160), 3840, 2160, 2)[0] == 4           # coarser texel step: 4 rows per thread
+    assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 4)[0] == 8
+    assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 3) == (0, 0)         # ssaa 3: tiled kernel
+    small = N.Uniforms.defaults(1920, 1080); small.extra[0][0] = 0.8
+    assert N.visualizer_plan(small, (1920, 1080), 1920, 1080, 1) == (0, 0)     # ~0.86 texel per fragment: tiled kernel
+    u.iCameraProjection = 2
+    assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 2) == (0, 0)         # equirectangular camera is not separable
+    u.iCameraProjection = 0; u.iCameraRight[1] = 0.1
+    assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 2) == (0, 0)         # rotated basis
