@@ -230,6 +230,10 @@ def other_configs(local: int) -> dict:
     scene.audio.load(synthetic.noise(2.0), 44100)
     ms = run(scene, 120, width=1920, height=1080, ssaa=1, subsample=2)
     out["configs[1] Visualizer 1920x1080 ssaa=1 subsample=2, white noise"] = dict(frames_per_s=120/(ms/1e3), ms_per_frame=ms/120, frames=120)
+    # configs[4]'s scene (8 concurrent exports are 8 independent replicas of this, one per GPU and sink)
+    scene = demo.PianoRoll(device=local); scene.initialize()
+    ms = run(scene, 120, width=3840, height=2160, ssaa=1, subsample=2)
+    out["configs[4] PianoRoll 3840x2160 ssaa=1 subsample=2, one export"] = dict(frames_per_s=120/(ms/1e3), ms_per_frame=ms/120, frames=120)
     for name, cls in (("Mandelbrot", demo.Mandelbrot), ("Tetration", demo.Tetration), ("RayMarch", demo.RayMarch)):
         scene = cls(device=local); scene.initialize()
         ms = run(scene, 2, warm=1, reps=1, width=7680, height=4320, ssaa=4, subsample=4)
@@ -362,6 +366,10 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
         line["other_configs"] = other_configs(local)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args)
+        from oracle import cpu_bench
+        r = cpu_bench.stft_sample()
+        line["stft"]["cpu_baseline"] = dict(value=r["msamples_per_s"], unit="Msamples/s", cores=1, kind="port",
+                                            sample=f"{r['frames']} frames of the numpy STFT -> filterbank -> dynamics port, one thread, {r['seconds']:.2f} s")
     print(json.dumps(line), file=RESULT, flush=True)
 
 

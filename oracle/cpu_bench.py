@@ -103,8 +103,8 @@ def stft_sample(seconds: float = 20.0) -> dict:
     """STFT→filterbank of the numpy port, one thread: Msamples/s consumed (hop·channels per frame)"""
     from oracle import audio_np as A
     cfg = A.TrackConfig(bank=A.BankConfig.from_notes(15, 129, piano=True))
-    clip = A.synth_chirp(5.0)
-    frames = 300
+    frames = int(seconds*60)
+    clip = A.synth_chirp(seconds)
     t0 = time.perf_counter()
     A.audio_track(clip, frames, cfg, waveform=False, scalars=False)
     dt = time.perf_counter() - t0
