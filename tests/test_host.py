@@ -229,3 +229,36 @@ def test_reference_example_files_run_unchanged_on_the_host_layer():
         assert scene.shader.scene_info["name"] == kernel, cls
         scene.main(width=64, height=36, time=0.05)           # host loop only (dry)
         assert scene.frame_index == 3
+
+
+def test_multi_program_scene_graphs_compile_without_a_gpu():
+    """The scenes of SURVEY §8f-2/3 on the dry backend: program / texture graph, kernel selection by directive,
+    sampler names and aliases of layered and temporal textures (texture.py:354-368), required uniforms"""
+    import examples.demo as demo
+    from shaderflow_b200.shader import ShaderProgram
+    expect = {
+        demo.MultiShader: {"iScreen": "multishader", "child": "multishader_child"},
+        demo.Multipass: {"iScreen": "multipass"}, demo.MotionBlur: {"iScreen": "motionblur"},
+        demo.Dynamics: {"iScreen": "dynamics"}, demo.Audio: {"iScreen": "audio"},
+        demo.Life: {"iScreen": "life_visuals", "iLife": "life_simulation"}, demo.PianoRoll: {"iScreen": "piano"},
+    }
+    for cls, programs in expect.items():
+        scene = cls(backend="dry"); scene.initialize()
+        found = {}
+        for module in scene.modules:
+            if isinstance(module, ShaderProgram) and not module.texture.final:
+                module.compile()
+                found[module.name] = module.scene_info["name"]
+                values, samplers = module.gather(scene.full_pipeline())
+                for name in module.scene_info["extra"]:
+                    assert name in values, (cls.__name__, name)
+                for name in module.scene_info["samplers"][:module.scene_info["required"]]:
+                    assert name in samplers, (cls.__name__, name)
+        assert found == programs, cls.__name__
+    blur = demo.MotionBlur(backend="dry"); blur.initialize()
+    names = blur.shader.texture.sampler_names()
+    assert {"iScreen0x0", "iScreen9x1", "iScreen", "iScreen3"} <= set(names) and len(blur.shader.texture.matrix) == 10
+    assert names["iScreen"] is blur.shader.texture.matrix[0][1] and names["iScreen3"] is blur.shader.texture.matrix[3][1]
+    life = demo.Life(backend="dry"); life.initialize()
+    assert life.simulation.texture.components == 1 and str(life.simulation.texture.dtype) == "float32"
+    assert {v.name: v.value for v in life.pipeline()}["iLifePeriod"] == 6
