@@ -150,20 +150,44 @@ __device__ __noinline__ void visualizer_unfitted(const RenderParams& P, int i, i
     rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
 }
 
-template <int S, int J>
 #ifndef VR_MIN_CTAS
 #define VR_MIN_CTAS 3
 #endif
+// VR_PACKED = 1 (experimental): bf16-pair window records (texel values and differences are
+// integers of magnitude <= 255, exact in bf16) — half the shared-memory bytes per gather — and fma.rn.f32x2 in
+// the vertical applications (accumulators as (r, g) pairs per row and (b_j, b_j+1) pairs per row pair).
+#ifndef VR_PACKED
+#define VR_PACKED 0
+#endif
+constexpr int VR_TEXEL_BYTES = VR_PACKED ? 12 : 24;            // window bytes per texel over both planes
+
+typedef unsigned long long vr_u64;
+SFB_DEV vr_u64 pack2(float lo, float hi) { vr_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+SFB_DEV void unpack2(vr_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SFB_DEV vr_u64 fma2(vr_u64 a, vr_u64 b, vr_u64 c) { vr_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// (value, difference) of one channel in one word: bf16(value) in the high half, bf16(difference) in the low half
+SFB_DEV unsigned int pack_bf16(float value, float diff) { return (__float_as_uint(value) & 0xffff0000u) | (__float_as_uint(diff) >> 16); }
+template <int S, int J>
 __global__ void __launch_bounds__(VR_THREADS, VR_MIN_CTAS)
 visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     static_assert(J % S == 0 && VR_COLS % S == 0, "a CTA shades whole output pixels");
     const RenderParams& P = VP.R;
     const int win_h = VP.win_h;
     extern __shared__ __align__(128) unsigned char vr_smem[];
+#if VR_PACKED
+    uint2* pa = reinterpret_cast<uint2*>(vr_smem);                                       // [win_h][64] (r | r'-r, g | g'-g) as bf16 pairs
+    unsigned int* pbw = reinterpret_cast<unsigned int*>(vr_smem + sizeof(uint2)*VR_WIN_W*win_h);   // [win_h][64] (b | b'-b)
+    unsigned char* tables = vr_smem + VR_TEXEL_BYTES*VR_WIN_W*win_h;
+    float4* tblQ = reinterpret_cast<float4*>(tables);                                    // [4][VR_HG][J/2] (h0_j, h0_j+1, h1_j, h1_j+1)
+    float2* tblW = reinterpret_cast<float2*>(tblQ + VR_GROUPS*VR_HG*(J/2));              // [4][VR_HG][J/2] (h2_j, h2_j+1)
+    float4* tblM = reinterpret_cast<float4*>(tblW + VR_GROUPS*VR_HG*(J/2));              // [4][VR_MAXQ][J/2][2] merged weights, rows (0,1) and (2,3)
+    __shared__ unsigned int rowoffS[VR_GROUPS][VR_HG];
+#else
     float4* rg = reinterpret_cast<float4*>(vr_smem);                                     // [win_h][64] (r, g, r'-r, g'-g)
     float2* bb = reinterpret_cast<float2*>(vr_smem + sizeof(float4)*VR_WIN_W*win_h);     // [win_h][64] (b, b'-b)
     float4* tblH = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][VR_HG][J] hinge weights + row offset
     float4* tblM = tblH + VR_GROUPS*VR_HG*J;                                             // [4][VR_MAXQ][J] merged weights of 4 texel rows
+#endif
     __shared__ float red[2][VR_THREADS/32];
     __shared__ float cyS[VR_GROUPS][J];
     __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
@@ -247,8 +271,17 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             if (!(t >= 0.0f && t <= float(VR_ROWS - 1)) || r0 < 0 || r0 + VR_ROWS > win_h) bad = 1;
             // byte offset of window row r0 in the (b, b'-b) plane, with the 2^23 exponent bits of the magic
             // floor of x folded in (modulo 2^32); the (r, g) plane uses twice this offset
+#if VR_PACKED
+            // byte offset of window row r0 in the 4-byte (b) plane; the 8-byte (r, g) plane uses twice this offset
+            const int slot = (g*VR_HG + k)*(J/2) + (r >> 1), odd = r & 1;
+            reinterpret_cast<float*>(tblQ + slot)[odd] = __saturatef(t);
+            reinterpret_cast<float*>(tblQ + slot)[2 + odd] = __saturatef(t - 1.0f);
+            reinterpret_cast<float*>(tblW + slot)[odd] = __saturatef(t - 2.0f);
+            if (r == 0) rowoffS[g][k] = (unsigned int)r0*(VR_WIN_W*4u) - (0x4B000000u << 2);
+#else
             const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
             tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+#endif
         }
         // merged weights of the dx = 0 taps: W[g][row][r] = sum over the 21 taps of hat(py - row), the
         // bilinear weight of texel row `row` (hat(t) = max(0, 1 - |t|)); one entry per loop trip
@@ -264,8 +297,17 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             float w = 0.0f;
             #pragma unroll 7
             for (int k = 0; k < VR_VTAPS; k++) w += fmaxf(1.0f - fabsf(fmaf(c_rows.vdy[k], scale, cy)), 0.0f);
+#if VR_PACKED
+            {   // rows (4q, 4q+1) of fragment rows (j, j+1) in one float4, rows (4q+2, 4q+3) in the next
+                const int c = row & 3;
+                float* quad = reinterpret_cast<float*>(tblM + (((g*VR_MAXQ + (row >> 2))*(J/2) + (r >> 1))*2 + (c >> 1)));
+                quad[(c & 1)*2 + (r & 1)] = w;
+            }
+            if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*4u) - (0x4B000000u << 2); mhdr[g][1] = (unsigned int)nq; }
+#else
             reinterpret_cast<float*>(tblM + (g*VR_MAXQ + (row >> 2))*J + r)[row & 3] = w;
             if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
+#endif
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
     }
@@ -302,8 +344,13 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             const int t = tid + k*VR_THREADS;
             if (t < n) {
                 const vec3 a = widen3(w0[k]), b = widen3(w1[k]);
+#if VR_PACKED
+                pa[t] = make_uint2(pack_bf16(a.x, b.x - a.x), pack_bf16(a.y, b.y - a.y));
+                pbw[t] = pack_bf16(a.z, b.z - a.z);
+#else
                 rg[t] = make_float4(a.x, a.y, b.x - a.x, b.y - a.y);
                 bb[t] = make_float2(a.z, b.z - a.z);
+#endif
             }
         }
     }
@@ -317,6 +364,104 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     for (int r = 0; r < J; r++) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; }
     if (fits && !(VP.debug & 1)) {
         const float cx = tapx - float(x0);                         // tile-local, >= 1 by construction of x0
+#if VR_PACKED
+        const char* paB = reinterpret_cast<const char*>(pa);
+        const char* pbB = reinterpret_cast<const char*>(pbw);
+        vr_u64 accRG[J], accB[J/2];                                  // (r, g) of row j; b of rows (2jp, 2jp+1)
+        #pragma unroll
+        for (int r = 0; r < J; r++) accRG[r] = 0ull;
+        #pragma unroll
+        for (int r = 0; r < J/2; r++) accB[r] = 0ull;
+        // Horizontal lerp of the 4 texel rows starting at byte offset `rowoff` (4-byte plane units), at column
+        // position cx + dx*scale: H[r] (+)= T + a*(T' - T); one 8-byte and one 4-byte load per row
+        auto gather = [&](float dx, unsigned int rowoff, float (&H)[VR_ROWS][3], const bool first) {
+            const float px = fmaf(dx, scale, cx);
+            const float tx_ = px + 8388607.5f;                       // magic floor, as in the unpacked path
+            const float a = px - (tx_ - 8388608.0f);
+            const unsigned int off4 = rowoff + (__float_as_uint(tx_) << 2);
+            const char* pr = paB + 2u*off4;
+            const char* pb = pbB + off4;
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS; r++) {
+                const uint2 q = *reinterpret_cast<const uint2*>(pr + r*(VR_WIN_W*8));
+                const unsigned int s = *reinterpret_cast<const unsigned int*>(pb + r*(VR_WIN_W*4));
+                const float vr = __uint_as_float(q.x & 0xffff0000u), dr = __uint_as_float(q.x << 16);
+                const float vg = __uint_as_float(q.y & 0xffff0000u), dg = __uint_as_float(q.y << 16);
+                const float vb = __uint_as_float(s & 0xffff0000u),   db = __uint_as_float(s << 16);
+                if (first) { H[r][0] = fmaf(a, dr, vr); H[r][1] = fmaf(a, dg, vg); H[r][2] = fmaf(a, db, vb); }
+                else { H[r][0] = fmaf(a, dr, H[r][0] + vr); H[r][1] = fmaf(a, dg, H[r][1] + vg); H[r][2] = fmaf(a, db, H[r][2] + vb); }
+            }
+        };
+        // Vertical interpolation of H for the J fragment rows: hinge weights of row pair jp in Q[jp] / Wt[jp]
+        auto apply = [&](const float4* Q, const float2* Wt, const float (&H)[VR_ROWS][3]) {
+            base0 += H[0][0]; base1 += H[0][1]; base2 += H[0][2];
+            vr_u64 Drg[VR_ROWS - 1], Db[VR_ROWS - 1];
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS - 1; r++) {
+                const float d2 = H[r + 1][2] - H[r][2];
+                Drg[r] = pack2(H[r + 1][0] - H[r][0], H[r + 1][1] - H[r][1]);
+                Db[r] = pack2(d2, d2);
+            }
+            #pragma unroll
+            for (int jp = 0; jp < J/2; jp++) {
+                const float4 w = Q[jp];
+                const float2 w2 = Wt[jp];
+                accRG[2*jp]     = fma2(Drg[0], pack2(w.x, w.x), fma2(Drg[1], pack2(w.z, w.z), fma2(Drg[2], pack2(w2.x, w2.x), accRG[2*jp])));
+                accRG[2*jp + 1] = fma2(Drg[0], pack2(w.y, w.y), fma2(Drg[1], pack2(w.w, w.w), fma2(Drg[2], pack2(w2.y, w2.y), accRG[2*jp + 1])));
+                accB[jp]        = fma2(Db[0], pack2(w.x, w.y), fma2(Db[1], pack2(w.z, w.w), fma2(Db[2], pack2(w2.x, w2.y), accB[jp])));
+            }
+        };
+
+        // phase 1: the dx = 0 taps through the merged weights, 4 texel rows at a time
+        {
+            const float4* M = tblM + ty*(VR_MAXQ*(J/2)*2);
+            unsigned int rowoff = mhdr[ty][0];
+            const int nq = int(mhdr[ty][1]);
+            #pragma unroll 1
+            for (int q = 0; q < nq; q++, rowoff += 4u*(VR_WIN_W*4u)) {
+                float H[VR_ROWS][3];
+                gather(0.0f, rowoff, H, true);
+                vr_u64 Hrg[VR_ROWS], Hb[VR_ROWS];
+                #pragma unroll
+                for (int r = 0; r < VR_ROWS; r++) { Hrg[r] = pack2(H[r][0], H[r][1]); Hb[r] = pack2(H[r][2], H[r][2]); }
+                #pragma unroll
+                for (int jp = 0; jp < J/2; jp++) {
+                    const float4 wa = M[(q*(J/2) + jp)*2], wb = M[(q*(J/2) + jp)*2 + 1];
+                    accRG[2*jp]     = fma2(Hrg[0], pack2(wa.x, wa.x), fma2(Hrg[1], pack2(wa.z, wa.z), fma2(Hrg[2], pack2(wb.x, wb.x), fma2(Hrg[3], pack2(wb.z, wb.z), accRG[2*jp]))));
+                    accRG[2*jp + 1] = fma2(Hrg[0], pack2(wa.y, wa.y), fma2(Hrg[1], pack2(wa.w, wa.w), fma2(Hrg[2], pack2(wb.y, wb.y), fma2(Hrg[3], pack2(wb.w, wb.w), accRG[2*jp + 1]))));
+                    accB[jp]        = fma2(Hb[0], pack2(wa.x, wa.y), fma2(Hb[1], pack2(wa.z, wa.w), fma2(Hb[2], pack2(wb.x, wb.y), fma2(Hb[3], pack2(wb.z, wb.w), accB[jp]))));
+                }
+            }
+        }
+        const float4* Q = tblQ + ty*(VR_HG*(J/2));
+        const float2* Wt = tblW + ty*(VR_HG*(J/2));
+        // phase 2: the dy = 0 taps; ray 0 is weighted twice
+        {
+            const unsigned int rowoff = rowoffS[ty][0];
+            float H[VR_ROWS][3];
+            gather(c_rows.hdx[0], rowoff, H, true);
+            #pragma unroll 3
+            for (int t = 1; t < 10; t++) gather(c_rows.hdx[t], rowoff, H, false);
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS; r++) { H[r][0] += H[r][0]; H[r][1] += H[r][1]; H[r][2] += H[r][2]; }
+            #pragma unroll 2
+            for (int t = 10; t < 20; t++) gather(c_rows.hdx[t], rowoff, H, false);
+            apply(Q, Wt, H);
+        }
+        // phase 3: the diagonal rays, two taps per vertical group
+        #pragma unroll 2
+        for (int p = 0; p < 20; p++) {
+            const unsigned int rowoff = rowoffS[ty][p + 1];
+            float H[VR_ROWS][3];
+            gather(c_rows.pdx[2*p], rowoff, H, true);
+            gather(c_rows.pdx[2*p + 1], rowoff, H, false);
+            apply(Q + (p + 1)*(J/2), Wt + (p + 1)*(J/2), H);
+        }
+        #pragma unroll
+        for (int r = 0; r < J; r++) unpack2(accRG[r], acc[r][0], acc[r][1]);
+        #pragma unroll
+        for (int jp = 0; jp < J/2; jp++) unpack2(accB[jp], acc[2*jp][2], acc[2*jp + 1][2]);
+#else
         const char* rgB = reinterpret_cast<const char*>(rg);
         const char* bbB = reinterpret_cast<const char*>(bb);
         // Horizontal lerp of the 4 texel rows starting at byte offset `rowoff` (b plane units), at column
@@ -399,6 +544,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             gather(c_rows.pdx[2*p + 1], rowoff, H, false);
             apply(Tp, e0, H);
         }
+#endif
     }
 
     // ---- E. rest of main() per fragment, 8-bit store rule per sub-sample, box sum --------------------
@@ -546,15 +692,20 @@ static std::atomic<unsigned int> g_next_slot{0};
 
 template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
     static bool configured = false;
+#if VR_PACKED
+    const size_t table = VR_GROUPS*VR_HG*(J/2)*(sizeof(float4) + sizeof(float2)) + sizeof(float4)*VR_GROUPS*VR_MAXQ*(J/2)*2;
+#else
     const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
+#endif
     const size_t epilogue = sizeof(float4)*J*VR_THREADS + size_t(VR_GROUPS*J)*VR_COLS*3;   // stash + rgb24 staging
     if (!configured) {
-        const size_t most = (sizeof(float4) + sizeof(float2))*VR_WIN_W*VR_MAX_H + table;
+        size_t most = size_t(VR_TEXEL_BYTES)*VR_WIN_W*VR_MAX_H + table;
+        if (most < epilogue) most = epilogue;
         cudaError_t e = cudaFuncSetAttribute(visualizer_rows_kernel<S, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    size_t smem = (sizeof(float4) + sizeof(float2))*VR_WIN_W*size_t(VP.win_h) + table;
+    size_t smem = size_t(VR_TEXEL_BYTES)*VR_WIN_W*size_t(VP.win_h) + table;
     if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
     // frame constants first (same stream): consecutive launches of the process rotate through the slots
