@@ -458,8 +458,10 @@ SFB_DEV vec4 scene_piano(const RenderParams& P, const Frag& f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// visualizer.frag, production path. Same mathematics as scene_visualizer (the literal transliteration
-// above stays as the parity anchor and serves SFB_FILTER_HARDWARE / unusual texture formats); what
+// visualizer.frag, per-fragment fast path (used where neither visualizer_rows.cu nor visualizer_tiled.cuh
+// applies: float32 debug outputs, targets that are not RGBA8, CTAs whose window does not fit). Same
+// mathematics as scene_visualizer (the literal transliteration above stays as the parity anchor and serves
+// SFB_FILTER_HARDWARE / unusual texture formats); what
 // changes is how the 91 bilinear taps of the blur loop (visualizer.frag:19-33) are evaluated:
 //   * the (angle, walk) pairs of the two strict-float32 loops are a 90-entry constant table
 //     (dir*walk), built on the host with the same float arithmetic (render.cu: build_blur_table);

@@ -1,6 +1,9 @@
-// visualizer_tiled.cuh — production kernel of the headline scene (examples/basic/shaders/visualizer.frag),
+// visualizer_tiled.cuh — per-pixel kernel of the headline scene (examples/basic/shaders/visualizer.frag),
 // fused with the SSAA downsample (fragment/final.glsl). One CTA shades a 32x8 tile of OUTPUT pixels
-// (S x S fragments each).
+// (S x S fragments each). It works for any camera; exports with the axis-aligned 2D camera and a fine enough
+// texel step go through the separable kernel instead (visualizer_rows.cu, 4.4x faster), this one takes the
+// rest: rotated / stereo / equirectangular cameras, ssaa 3, coarse steps, and the iScreen pass of unfused
+// exports (one fragment per thread, RGBA8 store with fragColor.a).
 //
 // What dominates visualizer.frag is the blur loop (:19-33): 1 + 90 bilinear taps of the background per
 // fragment, all inside a disc of `intensity` (<= 0.003 of the image height, i.e. <= 3.3 texels) around
