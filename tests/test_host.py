@@ -262,3 +262,21 @@ def test_multi_program_scene_graphs_compile_without_a_gpu():
     life = demo.Life(backend="dry"); life.initialize()
     assert life.simulation.texture.components == 1 and str(life.simulation.texture.dtype) == "float32"
     assert {v.name: v.value for v in life.pipeline()}["iLifePeriod"] == 6
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints exactly one JSON line with the
+    contract's keys; stdout carries nothing else"""
+    import json, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    done = subprocess.run([sys.executable, str(root/"bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--width", "640", "--height", "360"], capture_output=True, text=True, timeout=600)
+    assert done.returncode == 0, done.stderr[-2000:]
+    lines = [l for l in done.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["metric"] == "4K@2xSSAA music-visualizer frames/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == dict(value=line["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
