@@ -273,6 +273,15 @@ int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
                      sfb_tex* const* samplers, int n_samplers, int flags,
                      int width, int height, int ssaa, int subsample, int components, void* dst_dev);
 
+/* Parity probe of the fused path: the same kernels sfb_render_frame would pick (same flags, same launch) also
+ * store every shaded sub-sample's fragColor BEFORE the 8-bit iScreen store as float4 into screen_f32_dev
+ * [height*ssaa][width*ssaa][4] — what shader.py:367-375 would leave in a float FBO. Tests hold the production
+ * kernels to the reference GLSL's values at 1e-3 per channel with it; exports never call it. */
+int sfb_render_frame_probe(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                           sfb_tex* const* samplers, int n_samplers, int flags,
+                           int width, int height, int ssaa, int subsample, int components, void* dst_dev,
+                           float* screen_f32_dev);
+
 /* Which kernel sfb_render_frame picks for the visualizer scene (no GPU needed; diagnostics and tests):
  * *rows_per_thread = 8 or 4 when the separable kernel (one thread per fragment column) shades the frame and
  * *window_rows = background rows it stages per CTA; 0 when the per-pixel tiled kernel does (rotated / stereo /

@@ -111,6 +111,8 @@ _PROTOTYPES = dict(
     sfb_render_final=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_render_frame=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    sfb_render_frame_probe=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     sfb_pipe_open=(c_int, [c_void_p, c_int, c_int, c_size_t, POINTER(c_void_p)]),
     sfb_pipe_acquire=(c_int, [c_void_p, POINTER(c_void_p)]),
     sfb_pipe_submit=(c_int, [c_void_p, c_void_p]),
@@ -376,6 +378,13 @@ class Context:
                      ssaa: int, subsample: int, components: int, dst, flags: int = FILTER_EXACT) -> None:
         arr, n = self._samplers(textures)
         check(lib().sfb_render_frame(self.handle, scene, byref(uniforms), arr, n, flags, width, height, ssaa, subsample, components, _ptr(dst)))
+
+    def render_frame_probe(self, scene: int, uniforms: Uniforms, textures, width: int, height: int,
+                           ssaa: int, subsample: int, components: int, dst, screen_f32, flags: int = FILTER_EXACT) -> None:
+        """render_frame that also stores every sub-sample's pre-store fragColor as float4 (parity tests)"""
+        arr, n = self._samplers(textures)
+        check(lib().sfb_render_frame_probe(self.handle, scene, byref(uniforms), arr, n, flags, width, height, ssaa, subsample,
+                                           components, _ptr(dst), _ptr(screen_f32)))
 
     def destroy(self) -> None:
         if self.handle:

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(TILE_X*TILE_Y) frame_kernel(const __grid_const
             for (int sx = 0; sx < S; sx++) {
                 const Frag f = make_frag(P, x*S + sx, y*S + sy);
                 const vec4 c = shade<SCENE, HW>(P, f);
+                if (P.dst_f32)                                  // parity probe: fragColor before the 8-bit store
+                    reinterpret_cast<float4*>(P.dst_f32)[size_t(y*S + sy)*size_t(P.Wr) + size_t(x*S + sx)] = make_float4(c.x, c.y, c.z, c.w);
                 r += to_unorm8(c.x); g += to_unorm8(c.y); b += to_unorm8(c.z);
             }
         }
@@ -403,9 +405,9 @@ extern "C" int sfb_render_final(sfb_ctx* ctx, const void* screen_rgba8_dev, int 
     return SFB_OK;
 }
 
-extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
-                                sfb_tex* const* samplers, int n_samplers, int flags,
-                                int width, int height, int ssaa, int subsample, int components, void* dst_dev) {
+static int render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                        sfb_tex* const* samplers, int n_samplers, int flags,
+                        int width, int height, int ssaa, int subsample, int components, void* dst_dev, float* screen_f32_dev) {
     SFB_REQUIRE(ctx && dst_dev, "sfb_render_frame: null ctx or destination");
     SFB_REQUIRE(width > 0 && height > 0, "sfb_render_frame: bad size %dx%d", width, height);
     SFB_REQUIRE(ssaa >= 1 && ssaa <= 16, "sfb_render_frame: ssaa %d out of range", ssaa);
@@ -418,7 +420,7 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     P.W = width; P.H = height; P.ssaa = ssaa; P.subsample = subsample; P.comps = components;
     P.Wr = width*ssaa; P.Hr = height*ssaa;
     P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
-    P.dst = static_cast<unsigned char*>(dst_dev);
+    P.dst = static_cast<unsigned char*>(dst_dev); P.dst_f32 = screen_f32_dev;
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && ssaa <= 4) {
         // production path of the headline scene: the separable kernel when the camera allows it, ...
         if (!(flags & SFB_RENDER_TILED)) {
@@ -446,4 +448,18 @@ extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uni
     dispatch<LaunchFrame>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
+}
+
+extern "C" int sfb_render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                                sfb_tex* const* samplers, int n_samplers, int flags,
+                                int width, int height, int ssaa, int subsample, int components, void* dst_dev) {
+    return render_frame(ctx, scene, uniforms, samplers, n_samplers, flags, width, height, ssaa, subsample, components, dst_dev, nullptr);
+}
+
+extern "C" int sfb_render_frame_probe(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
+                                      sfb_tex* const* samplers, int n_samplers, int flags,
+                                      int width, int height, int ssaa, int subsample, int components, void* dst_dev,
+                                      float* screen_f32_dev) {
+    SFB_REQUIRE(screen_f32_dev, "sfb_render_frame_probe: null float target");
+    return render_frame(ctx, scene, uniforms, samplers, n_samplers, flags, width, height, ssaa, subsample, components, dst_dev, screen_f32_dev);
 }

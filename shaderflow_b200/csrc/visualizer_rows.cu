@@ -604,6 +604,8 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
                 c = (VP.debug & 2) ? mk3(q.x, q.y, q.z)
                                    : vis_back_sep(P, K, sc, mk3(q.x, q.y, q.z), agx, asx, uvx, wavx, wavy, row.x, row.y, row.z);
             }
+            if (P.dst_f32 && col_in && jb + r < P.Hr)              // parity probe: fragColor before the 8-bit store
+                reinterpret_cast<float4*>(P.dst_f32)[size_t(jb + r)*size_t(P.Wr) + size_t(i)] = make_float4(c.x, c.y, c.z, vc.oob ? 0.0f : 1.0f);
             r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
             g8 += (unsigned int)__float2int_rn(__saturatef(c.y)*255.0f);
             b8 += (unsigned int)__float2int_rn(__saturatef(c.z)*255.0f);

@@ -276,6 +276,8 @@ visualizer_tiled_kernel(const __grid_constant__ VisualizerParams VP) {
                 footprint(0.0f, 0.0f);                                  // the undisplaced first tap (visualizer.frag:18)
                 c = vis_back(P, v, mk3(ar, ag, ab)*((1.0f/255.0f)/(10.0f*8.0f)));
             }
+            if (P.dst_f32)                                              // parity probe: fragColor before the 8-bit store
+                reinterpret_cast<float4*>(P.dst_f32)[size_t(y*S + (s / S))*size_t(P.Wr) + size_t(x*S + (s % S))] = make_float4(c.x, c.y, c.z, c.w);
             r8 += (unsigned int)__float2int_rn(__saturatef(c.x)*255.0f);
             g8 += (unsigned int)__float2int_rn(__saturatef(c.y)*255.0f);
             b8 += (unsigned int)__float2int_rn(__saturatef(c.z)*255.0f);
