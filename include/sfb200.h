@@ -308,6 +308,33 @@ int sfb_pipe_sync(sfb_pipe* pipe);                       /* blocks until every s
 int sfb_pipe_stats(sfb_pipe* pipe, uint64_t* frames, uint64_t* bytes);
 int sfb_pipe_close(sfb_pipe* pipe);
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Sink of a frame-SHARDED export (same role as the ring above, exporting.py:140-174, when the
+ * export runs as one process per GPU). One shared-memory segment holds a host ring of `slots` frames per rank;
+ * every rank pins its own ring and copies its frames device → host over ITS OWN PCIe link while it shades;
+ * ownership is block-cyclic (frame g belongs to rank (g / block) % world); rank 0's writer thread walks the
+ * frames in time order and write()s them to the sink's fd. Cross-process state = two counters per rank in the
+ * segment header; no collective, no kernel.
+ *   open:   rank 0 passes segment_path NULL and creates the segment; the others attach to sfb_sink_path(rank 0's).
+ *           ctx NULL = host-only sink (frames handed over as host memory; CPU tests of the protocol).
+ *   begin:  every rank, then the caller synchronises the ranks before the first frame (rank 0 resets the
+ *           counters and starts the writer; fd < 0 = null sink).
+ *   acquire / submit: like sfb_pipe_*, for the frames THIS rank owns, in time order.
+ *   finish: blocks until this rank's frames have left (rank 0: until the whole export is written).
+ *   abort:  unblocks every rank with an error. */
+typedef struct sfb_sink sfb_sink;
+int sfb_sink_open(sfb_ctx* ctx, const char* segment_path, int rank, int world, int slots,
+                  size_t frame_bytes, sfb_sink** out);
+const char* sfb_sink_path(sfb_sink* sink);
+int sfb_sink_begin(sfb_sink* sink, int64_t total_frames, int block, int fd);
+int sfb_sink_owner(sfb_sink* sink, int64_t frame, int* owner);
+int sfb_sink_acquire(sfb_sink* sink, void** frame_dev);
+int sfb_sink_submit(sfb_sink* sink);
+int sfb_sink_submit_host(sfb_sink* sink, const void* frame_host);
+int sfb_sink_finish(sfb_sink* sink, uint64_t* frames, uint64_t* bytes);
+int sfb_sink_abort(sfb_sink* sink);
+int sfb_sink_close(sfb_sink* sink);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,11 @@ def small_cases() -> list[Case]:
         Case("visualizer_quiet", "Visualizer", "iScreen", "visualizer",
              U(W, H, ssaa=1.0, iTime=7.7, iTau=0.77, extra=dict(iAudioVolume=0.05, iAudioSTD=0.0)),
              visualizer_tex(bg, seed=4), ssaa=1.0, final=(2,)),
+        # the reference's default export: ssaa 1, subsample 2, target at the background's own resolution (~0.8 texel
+        # per fragment: the separable kernel's 96-texel-window variant, then the unfused final pass)
+        Case("visualizer_native", "Visualizer", "iScreen", "visualizer",
+             U(96, 54, ssaa=1.0, iTime=2.2, iTau=0.22, extra=dict(iAudioVolume=0.9, iAudioSTD=0.3)),
+             visualizer_tex(background(96, 54), seed=9), W=96, H=54, ssaa=1.0, final=(2,)),
         Case("visualizer_pillarbox", "Visualizer", "iScreen", "visualizer",
              U(W, H, iTime=3.3, iTau=0.33, iWantAspect=1.0, extra=dict(iAudioVolume=0.4, iAudioSTD=0.6)),
              visualizer_tex(bg, seed=5)),

@@ -120,6 +120,16 @@ _PROTOTYPES = dict(
     sfb_pipe_sync=(c_int, [c_void_p]),
     sfb_pipe_stats=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     sfb_pipe_close=(c_int, [c_void_p]),
+    sfb_sink_open=(c_int, [c_void_p, c_char_p, c_int, c_int, c_int, c_size_t, POINTER(c_void_p)]),
+    sfb_sink_path=(c_char_p, [c_void_p]),
+    sfb_sink_begin=(c_int, [c_void_p, c_int64, c_int, c_int]),
+    sfb_sink_owner=(c_int, [c_void_p, c_int64, POINTER(c_int)]),
+    sfb_sink_acquire=(c_int, [c_void_p, POINTER(c_void_p)]),
+    sfb_sink_submit=(c_int, [c_void_p]),
+    sfb_sink_submit_host=(c_int, [c_void_p, c_void_p]),
+    sfb_sink_finish=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
+    sfb_sink_abort=(c_int, [c_void_p]),
+    sfb_sink_close=(c_int, [c_void_p]),
 )
 
 _lib = None
@@ -286,6 +296,51 @@ class Pipe:
         if self.handle:
             handle, self.handle = self.handle, c_void_p()
             check(lib().sfb_pipe_close(handle))
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
+class SharedSink:
+    """sfb_sink handle: this rank's share of the sharded export's host ring (csrc/sink.cu). `ctx` None = host-only"""
+    def __init__(self, ctx: "Context | None", path: str | None, rank: int, world: int, slots: int, frame_bytes: int):
+        self.ctx, self.handle = ctx, c_void_p()
+        self.rank, self.world, self.slots, self.frame_bytes = rank, world, slots, frame_bytes
+        check(lib().sfb_sink_open(ctx.handle if ctx is not None else None, path.encode() if path else None,
+                                  rank, world, slots, frame_bytes, byref(self.handle)))
+
+    @property
+    def path(self) -> str:
+        return lib().sfb_sink_path(self.handle).decode()
+
+    def begin(self, total_frames: int, block: int, fd: int = -1) -> None:
+        check(lib().sfb_sink_begin(self.handle, total_frames, block, fd))
+
+    def acquire(self) -> int:
+        p = c_void_p()
+        check(lib().sfb_sink_acquire(self.handle, byref(p)))
+        return p.value
+
+    def submit(self) -> None:
+        check(lib().sfb_sink_submit(self.handle))
+
+    def submit_host(self, frame=None) -> None:
+        check(lib().sfb_sink_submit_host(self.handle, _ptr(frame)))
+
+    def finish(self) -> tuple[int, int]:
+        f, b = c_uint64(), c_uint64()
+        check(lib().sfb_sink_finish(self.handle, byref(f), byref(b)))
+        return f.value, b.value
+
+    def abort(self) -> None:
+        if self.handle:
+            lib().sfb_sink_abort(self.handle)
+
+    def close(self) -> None:
+        if self.handle:
+            handle, self.handle = self.handle, c_void_p()
+            check(lib().sfb_sink_close(handle))
 
     def __del__(self):
         try: self.close()

@@ -203,8 +203,20 @@ class ShaderCamera(ShaderModule):
             self.apply_zoom(-0.05*message.dy)
 
     # -- basis ---------------------------------------------------------------------------------
+    _basis_cache: dict = None
+
     def _basis(self, vector, which: str) -> np.ndarray:
-        return Algebra.rotate_vector(vector, getattr(self.rotation, which))
+        """Rotated basis vector; cached on the rotation's value (an export with a still camera asks for the
+        same three vectors every frame)"""
+        rotation = getattr(self.rotation, which)
+        key = (which, vector.tobytes(), np.asarray(rotation, dtype=np.float64).tobytes())
+        cache = self._basis_cache
+        if cache is None or len(cache) > 64:
+            cache = self._basis_cache = {}
+        hit = cache.get(key)
+        if hit is None:
+            hit = cache[key] = Algebra.rotate_vector(vector, rotation)
+        return hit.copy()
 
     right           = property(lambda s: s._basis(GlobalBasis.Right, "value"))
     right_target    = property(lambda s: s._basis(GlobalBasis.Right, "target"))

@@ -42,17 +42,20 @@ static void writer_loop(sfb_pipe* p) {
             slot = &p->slots[p->tail % p->slots.size()];
         }
         cudaEventSynchronize(slot->copied);
-        if (p->fd >= 0 && !p->io_errno) {
+        int fd, failed;
+        { std::lock_guard<std::mutex> lock(p->mu); fd = p->fd; failed = p->io_errno; }
+        if (fd >= 0 && !failed) {
             const char* src = static_cast<const char*>(slot->host);
             size_t left = p->frame_bytes;
             while (left) {
-                ssize_t n = ::write(p->fd, src, left);
-                if (n < 0) { if (errno == EINTR) continue; p->io_errno = errno; break; }
+                ssize_t n = ::write(fd, src, left);
+                if (n < 0) { if (errno == EINTR) continue; failed = errno; break; }
                 src += n; left -= size_t(n);
             }
         }
         {
             std::lock_guard<std::mutex> lock(p->mu);
+            if (failed) p->io_errno = failed;
             slot->state = 0; p->tail++; p->written++; p->bytes += p->frame_bytes;
         }
         p->cv.notify_all();

@@ -325,11 +325,13 @@ static const CUtensorMap* background_tensor_map(sfb_tex* t) {
 }
 
 template <int S> static cudaError_t launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};                      // the attribute is per device
+    int device = 0;
+    if (cudaError_t e = cudaGetDevice(&device); e != cudaSuccess) return e;
+    if (device >= 64 || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(visualizer_tiled_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VT_SMEM));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (device < 64) configured[device] = true;
     }
     dim3 block(VT_TILE_X, VT_TILE_Y), grid((VP.R.W + VT_TILE_X - 1)/VT_TILE_X, (VP.R.H + VT_TILE_Y - 1)/VT_TILE_Y);
     visualizer_tiled_kernel<S><<<grid, block, VT_SMEM, st>>>(VP);
@@ -339,10 +341,15 @@ template <int S> static cudaError_t launch_visualizer_tiled(const VisualizerPara
 // The iScreen pass of an unfused visualizer export (the reference's default ssaa=1, subsample=2 blends
 // neighbours in final.glsl, so K3 and K4 stay separate): the tiled kernel with one fragment per thread and an
 // RGBA8 store that keeps fragColor.a
-static int visualizer_screen_pass(sfb_ctx* ctx, const RenderParams& P, sfb_tex* background) {
+static int visualizer_screen_pass(sfb_ctx* ctx, const RenderParams& P, sfb_tex* background, int flags) {
     VisualizerParams VP;
     VP.R = P;
     VP.R.W = P.Wr; VP.R.H = P.Hr; VP.R.ssaa = 1; VP.R.subsample = 1; VP.R.comps = 4;
+    if (!(flags & SFB_RENDER_TILED)) {            // the separable kernel, one fragment per "output pixel", alpha kept
+        int launched = 0;
+        if (int e = sfb_visualizer_rows_launch(VP.R, ctx->stream, &launched, 1)) return e;
+        if (launched) { ctx->launches += launched - 1; SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
+    }
     VP.tmap = background_tensor_map(background);
     VP.use_tma = VP.tmap ? 1 : 0;
     VP.screen_alpha = 1;
@@ -364,7 +371,7 @@ extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.dst = static_cast<unsigned char*>(dst_rgba8_dev); P.dst_f32 = dst_f32_dev;
     P.dst_dtype = SFB_DTYPE_U8; P.dst_padded = 4;
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && !dst_f32_dev)
-        return visualizer_screen_pass(ctx, P, samplers[0]);
+        return visualizer_screen_pass(ctx, P, samplers[0], flags);
     dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
@@ -385,7 +392,7 @@ extern "C" int sfb_render_target(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.dst_dtype = target->dtype; P.dst_padded = target->padded;
     target->array_stale = true;                   // the cudaArray copy is old: sample through the linear mirror
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && target->dtype == SFB_DTYPE_U8 && target->padded == 4)
-        return visualizer_screen_pass(ctx, P, samplers[0]);
+        return visualizer_screen_pass(ctx, P, samplers[0], flags);
     dispatch<LaunchScreen>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;

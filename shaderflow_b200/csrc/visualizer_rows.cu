@@ -45,7 +45,7 @@ namespace glsl {
 constexpr int VR_COLS = 64;            // fragment columns per CTA (threadIdx.x)
 constexpr int VR_GROUPS = 4;           // row groups per CTA (threadIdx.y)
 constexpr int VR_THREADS = VR_COLS*VR_GROUPS;
-constexpr int VR_WIN_W = 64;           // window row stride, texels
+constexpr int VR_WIN_MAX = 96;         // widest window row stride (texels) a variant uses: 64 or 96
 constexpr int VR_MAX_H = 40;           // window rows the launcher may ask for
 constexpr int VR_ROWS = 4;             // texel rows interpolated per tap: covers a vertical span < 2 texels
 constexpr int VR_HG = 21;              // vertical (hinge) groups: 0 = rays 0°/180°, 1-10 = rays 45°/135°, 11-20 = rays 225°/315°
@@ -65,6 +65,7 @@ struct VisRowsParams {
     int win_h;                         // window rows staged (dynamic shared memory is sized for it)
     int slot;                          // g_frame entry written by visualizer_frame_consts_kernel for this frame
     int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
+    int screen_alpha;                  // comps == 4: store fragColor.a (iScreen pass of an unfused export) instead of 255
 };
 
 SFB_DEV void bulk_load_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
@@ -153,41 +154,24 @@ __device__ __noinline__ void visualizer_unfitted(const RenderParams& P, int i, i
 #ifndef VR_MIN_CTAS
 #define VR_MIN_CTAS 3
 #endif
-// VR_PACKED = 1 (experimental): bf16-pair window records (texel values and differences are
-// integers of magnitude <= 255, exact in bf16) — half the shared-memory bytes per gather — and fma.rn.f32x2 in
-// the vertical applications (accumulators as (r, g) pairs per row and (b_j, b_j+1) pairs per row pair).
-#ifndef VR_PACKED
-#define VR_PACKED 0
-#endif
-constexpr int VR_TEXEL_BYTES = VR_PACKED ? 12 : 24;            // window bytes per texel over both planes
+constexpr int VR_TEXEL_BYTES = 24;                             // window bytes per texel over both planes
+constexpr int vr_max_h(int ww) { return ww == 64 ? VR_MAX_H : 32; }     // window rows a variant may stage
 
-typedef unsigned long long vr_u64;
-SFB_DEV vr_u64 pack2(float lo, float hi) { vr_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-SFB_DEV void unpack2(vr_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-SFB_DEV vr_u64 fma2(vr_u64 a, vr_u64 b, vr_u64 c) { vr_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-// (value, difference) of one channel in one word: bf16(value) in the high half, bf16(difference) in the low half
-SFB_DEV unsigned int pack_bf16(float value, float diff) { return (__float_as_uint(value) & 0xffff0000u) | (__float_as_uint(diff) >> 16); }
-template <int S, int J>
+// S = ssaa (sub-samples per output pixel and axis), J = fragment rows per thread, WW = window row stride in texels
+// (64 when the horizontal texel step per fragment is small, 96 up to ~1 texel per fragment: the reference's default
+// export, ssaa = 1 at the background's own resolution)
+template <int S, int J, int WW>
 __global__ void __launch_bounds__(VR_THREADS, VR_MIN_CTAS)
 visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     static_assert(J % S == 0 && VR_COLS % S == 0, "a CTA shades whole output pixels");
+    constexpr int VR_WIN_W = WW;
     const RenderParams& P = VP.R;
     const int win_h = VP.win_h;
     extern __shared__ __align__(128) unsigned char vr_smem[];
-#if VR_PACKED
-    uint2* pa = reinterpret_cast<uint2*>(vr_smem);                                       // [win_h][64] (r | r'-r, g | g'-g) as bf16 pairs
-    unsigned int* pbw = reinterpret_cast<unsigned int*>(vr_smem + sizeof(uint2)*VR_WIN_W*win_h);   // [win_h][64] (b | b'-b)
-    unsigned char* tables = vr_smem + VR_TEXEL_BYTES*VR_WIN_W*win_h;
-    float4* tblQ = reinterpret_cast<float4*>(tables);                                    // [4][VR_HG][J/2] (h0_j, h0_j+1, h1_j, h1_j+1)
-    float2* tblW = reinterpret_cast<float2*>(tblQ + VR_GROUPS*VR_HG*(J/2));              // [4][VR_HG][J/2] (h2_j, h2_j+1)
-    float4* tblM = reinterpret_cast<float4*>(tblW + VR_GROUPS*VR_HG*(J/2));              // [4][VR_MAXQ][J/2][2] merged weights, rows (0,1) and (2,3)
-    __shared__ unsigned int rowoffS[VR_GROUPS][VR_HG];
-#else
     float4* rg = reinterpret_cast<float4*>(vr_smem);                                     // [win_h][64] (r, g, r'-r, g'-g)
     float2* bb = reinterpret_cast<float2*>(vr_smem + sizeof(float4)*VR_WIN_W*win_h);     // [win_h][64] (b, b'-b)
     float4* tblH = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][VR_HG][J] hinge weights + row offset
     float4* tblM = tblH + VR_GROUPS*VR_HG*J;                                             // [4][VR_MAXQ][J] merged weights of 4 texel rows
-#endif
     __shared__ float red[2][VR_THREADS/32];
     __shared__ float cyS[VR_GROUPS][J];
     __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
@@ -271,17 +255,8 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             if (!(t >= 0.0f && t <= float(VR_ROWS - 1)) || r0 < 0 || r0 + VR_ROWS > win_h) bad = 1;
             // byte offset of window row r0 in the (b, b'-b) plane, with the 2^23 exponent bits of the magic
             // floor of x folded in (modulo 2^32); the (r, g) plane uses twice this offset
-#if VR_PACKED
-            // byte offset of window row r0 in the 4-byte (b) plane; the 8-byte (r, g) plane uses twice this offset
-            const int slot = (g*VR_HG + k)*(J/2) + (r >> 1), odd = r & 1;
-            reinterpret_cast<float*>(tblQ + slot)[odd] = __saturatef(t);
-            reinterpret_cast<float*>(tblQ + slot)[2 + odd] = __saturatef(t - 1.0f);
-            reinterpret_cast<float*>(tblW + slot)[odd] = __saturatef(t - 2.0f);
-            if (r == 0) rowoffS[g][k] = (unsigned int)r0*(VR_WIN_W*4u) - (0x4B000000u << 2);
-#else
             const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
             tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
-#endif
         }
         // merged weights of the dx = 0 taps: W[g][row][r] = sum over the 21 taps of hat(py - row), the
         // bilinear weight of texel row `row` (hat(t) = max(0, 1 - |t|)); one entry per loop trip
@@ -297,24 +272,15 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             float w = 0.0f;
             #pragma unroll 7
             for (int k = 0; k < VR_VTAPS; k++) w += fmaxf(1.0f - fabsf(fmaf(c_rows.vdy[k], scale, cy)), 0.0f);
-#if VR_PACKED
-            {   // rows (4q, 4q+1) of fragment rows (j, j+1) in one float4, rows (4q+2, 4q+3) in the next
-                const int c = row & 3;
-                float* quad = reinterpret_cast<float*>(tblM + (((g*VR_MAXQ + (row >> 2))*(J/2) + (r >> 1))*2 + (c >> 1)));
-                quad[(c & 1)*2 + (r & 1)] = w;
-            }
-            if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*4u) - (0x4B000000u << 2); mhdr[g][1] = (unsigned int)nq; }
-#else
             reinterpret_cast<float*>(tblM + (g*VR_MAXQ + (row >> 2))*J + r)[row & 3] = w;
             if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
-#endif
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
     }
 
     // ---- B2. widen the window into pre-differenced pair records -------------------------------------
     if (window_ok) {
-        constexpr int PER = (VR_WIN_W*VR_MAX_H + VR_THREADS - 1)/VR_THREADS;
+        constexpr int PER = (VR_WIN_W*vr_max_h(WW) + VR_THREADS - 1)/VR_THREADS;
         unsigned int w0[PER], w1[PER];
         const int n = VR_WIN_W*win_h;
         if (tma) {
@@ -344,13 +310,8 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             const int t = tid + k*VR_THREADS;
             if (t < n) {
                 const vec3 a = widen3(w0[k]), b = widen3(w1[k]);
-#if VR_PACKED
-                pa[t] = make_uint2(pack_bf16(a.x, b.x - a.x), pack_bf16(a.y, b.y - a.y));
-                pbw[t] = pack_bf16(a.z, b.z - a.z);
-#else
                 rg[t] = make_float4(a.x, a.y, b.x - a.x, b.y - a.y);
                 bb[t] = make_float2(a.z, b.z - a.z);
-#endif
             }
         }
     }
@@ -364,104 +325,6 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     for (int r = 0; r < J; r++) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; }
     if (fits && !(VP.debug & 1)) {
         const float cx = tapx - float(x0);                         // tile-local, >= 1 by construction of x0
-#if VR_PACKED
-        const char* paB = reinterpret_cast<const char*>(pa);
-        const char* pbB = reinterpret_cast<const char*>(pbw);
-        vr_u64 accRG[J], accB[J/2];                                  // (r, g) of row j; b of rows (2jp, 2jp+1)
-        #pragma unroll
-        for (int r = 0; r < J; r++) accRG[r] = 0ull;
-        #pragma unroll
-        for (int r = 0; r < J/2; r++) accB[r] = 0ull;
-        // Horizontal lerp of the 4 texel rows starting at byte offset `rowoff` (4-byte plane units), at column
-        // position cx + dx*scale: H[r] (+)= T + a*(T' - T); one 8-byte and one 4-byte load per row
-        auto gather = [&](float dx, unsigned int rowoff, float (&H)[VR_ROWS][3], const bool first) {
-            const float px = fmaf(dx, scale, cx);
-            const float tx_ = px + 8388607.5f;                       // magic floor, as in the unpacked path
-            const float a = px - (tx_ - 8388608.0f);
-            const unsigned int off4 = rowoff + (__float_as_uint(tx_) << 2);
-            const char* pr = paB + 2u*off4;
-            const char* pb = pbB + off4;
-            #pragma unroll
-            for (int r = 0; r < VR_ROWS; r++) {
-                const uint2 q = *reinterpret_cast<const uint2*>(pr + r*(VR_WIN_W*8));
-                const unsigned int s = *reinterpret_cast<const unsigned int*>(pb + r*(VR_WIN_W*4));
-                const float vr = __uint_as_float(q.x & 0xffff0000u), dr = __uint_as_float(q.x << 16);
-                const float vg = __uint_as_float(q.y & 0xffff0000u), dg = __uint_as_float(q.y << 16);
-                const float vb = __uint_as_float(s & 0xffff0000u),   db = __uint_as_float(s << 16);
-                if (first) { H[r][0] = fmaf(a, dr, vr); H[r][1] = fmaf(a, dg, vg); H[r][2] = fmaf(a, db, vb); }
-                else { H[r][0] = fmaf(a, dr, H[r][0] + vr); H[r][1] = fmaf(a, dg, H[r][1] + vg); H[r][2] = fmaf(a, db, H[r][2] + vb); }
-            }
-        };
-        // Vertical interpolation of H for the J fragment rows: hinge weights of row pair jp in Q[jp] / Wt[jp]
-        auto apply = [&](const float4* Q, const float2* Wt, const float (&H)[VR_ROWS][3]) {
-            base0 += H[0][0]; base1 += H[0][1]; base2 += H[0][2];
-            vr_u64 Drg[VR_ROWS - 1], Db[VR_ROWS - 1];
-            #pragma unroll
-            for (int r = 0; r < VR_ROWS - 1; r++) {
-                const float d2 = H[r + 1][2] - H[r][2];
-                Drg[r] = pack2(H[r + 1][0] - H[r][0], H[r + 1][1] - H[r][1]);
-                Db[r] = pack2(d2, d2);
-            }
-            #pragma unroll
-            for (int jp = 0; jp < J/2; jp++) {
-                const float4 w = Q[jp];
-                const float2 w2 = Wt[jp];
-                accRG[2*jp]     = fma2(Drg[0], pack2(w.x, w.x), fma2(Drg[1], pack2(w.z, w.z), fma2(Drg[2], pack2(w2.x, w2.x), accRG[2*jp])));
-                accRG[2*jp + 1] = fma2(Drg[0], pack2(w.y, w.y), fma2(Drg[1], pack2(w.w, w.w), fma2(Drg[2], pack2(w2.y, w2.y), accRG[2*jp + 1])));
-                accB[jp]        = fma2(Db[0], pack2(w.x, w.y), fma2(Db[1], pack2(w.z, w.w), fma2(Db[2], pack2(w2.x, w2.y), accB[jp])));
-            }
-        };
-
-        // phase 1: the dx = 0 taps through the merged weights, 4 texel rows at a time
-        {
-            const float4* M = tblM + ty*(VR_MAXQ*(J/2)*2);
-            unsigned int rowoff = mhdr[ty][0];
-            const int nq = int(mhdr[ty][1]);
-            #pragma unroll 1
-            for (int q = 0; q < nq; q++, rowoff += 4u*(VR_WIN_W*4u)) {
-                float H[VR_ROWS][3];
-                gather(0.0f, rowoff, H, true);
-                vr_u64 Hrg[VR_ROWS], Hb[VR_ROWS];
-                #pragma unroll
-                for (int r = 0; r < VR_ROWS; r++) { Hrg[r] = pack2(H[r][0], H[r][1]); Hb[r] = pack2(H[r][2], H[r][2]); }
-                #pragma unroll
-                for (int jp = 0; jp < J/2; jp++) {
-                    const float4 wa = M[(q*(J/2) + jp)*2], wb = M[(q*(J/2) + jp)*2 + 1];
-                    accRG[2*jp]     = fma2(Hrg[0], pack2(wa.x, wa.x), fma2(Hrg[1], pack2(wa.z, wa.z), fma2(Hrg[2], pack2(wb.x, wb.x), fma2(Hrg[3], pack2(wb.z, wb.z), accRG[2*jp]))));
-                    accRG[2*jp + 1] = fma2(Hrg[0], pack2(wa.y, wa.y), fma2(Hrg[1], pack2(wa.w, wa.w), fma2(Hrg[2], pack2(wb.y, wb.y), fma2(Hrg[3], pack2(wb.w, wb.w), accRG[2*jp + 1]))));
-                    accB[jp]        = fma2(Hb[0], pack2(wa.x, wa.y), fma2(Hb[1], pack2(wa.z, wa.w), fma2(Hb[2], pack2(wb.x, wb.y), fma2(Hb[3], pack2(wb.z, wb.w), accB[jp]))));
-                }
-            }
-        }
-        const float4* Q = tblQ + ty*(VR_HG*(J/2));
-        const float2* Wt = tblW + ty*(VR_HG*(J/2));
-        // phase 2: the dy = 0 taps; ray 0 is weighted twice
-        {
-            const unsigned int rowoff = rowoffS[ty][0];
-            float H[VR_ROWS][3];
-            gather(c_rows.hdx[0], rowoff, H, true);
-            #pragma unroll 3
-            for (int t = 1; t < 10; t++) gather(c_rows.hdx[t], rowoff, H, false);
-            #pragma unroll
-            for (int r = 0; r < VR_ROWS; r++) { H[r][0] += H[r][0]; H[r][1] += H[r][1]; H[r][2] += H[r][2]; }
-            #pragma unroll 2
-            for (int t = 10; t < 20; t++) gather(c_rows.hdx[t], rowoff, H, false);
-            apply(Q, Wt, H);
-        }
-        // phase 3: the diagonal rays, two taps per vertical group
-        #pragma unroll 2
-        for (int p = 0; p < 20; p++) {
-            const unsigned int rowoff = rowoffS[ty][p + 1];
-            float H[VR_ROWS][3];
-            gather(c_rows.pdx[2*p], rowoff, H, true);
-            gather(c_rows.pdx[2*p + 1], rowoff, H, false);
-            apply(Q + (p + 1)*(J/2), Wt + (p + 1)*(J/2), H);
-        }
-        #pragma unroll
-        for (int r = 0; r < J; r++) unpack2(accRG[r], acc[r][0], acc[r][1]);
-        #pragma unroll
-        for (int jp = 0; jp < J/2; jp++) unpack2(accB[jp], acc[2*jp][2], acc[2*jp + 1][2]);
-#else
         const char* rgB = reinterpret_cast<const char*>(rg);
         const char* bbB = reinterpret_cast<const char*>(bb);
         // Horizontal lerp of the 4 texel rows starting at byte offset `rowoff` (b plane units), at column
@@ -544,7 +407,6 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             gather(c_rows.pdx[2*p + 1], rowoff, H, false);
             apply(Tp, e0, H);
         }
-#endif
     }
 
     // ---- E. rest of main() per fragment, 8-bit store rule per sub-sample, box sum --------------------
@@ -590,6 +452,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     #pragma unroll (S == 1 ? 2 : 1)
     for (int pr = 0; pr < J/S; pr++) {
         unsigned int r8 = 0, g8 = 0, b8 = 0;
+        const unsigned int a8 = (VP.screen_alpha && vc.oob) ? 0u : 255u;      // visualizer.frag:11-14 leaves alpha unwritten
         #pragma unroll (S >= 2 ? 2 : 1)
         for (int s = 0; s < S; s++) {
             const int r = pr*S + s;
@@ -621,7 +484,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         const int y = (jb + pr*S)/S, x = i/S;                      // output pixel
         if ((tx % S) == 0 && col_in && y < P.H) {
             if (P.comps == 4) {
-                reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
+                reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, a8);
             } else if (!words) {
                 unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r8; p[1] = g8; p[2] = b8;
             } else {
@@ -692,29 +555,27 @@ static int build_rows_tables() {
 
 static std::atomic<unsigned int> g_next_slot{0};
 
-template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
-    static bool configured = false;
-#if VR_PACKED
-    const size_t table = VR_GROUPS*VR_HG*(J/2)*(sizeof(float4) + sizeof(float2)) + sizeof(float4)*VR_GROUPS*VR_MAXQ*(J/2)*2;
-#else
+template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
+    static bool configured[64] = {};                      // the attribute is per device
+    int device = 0;
+    if (cudaError_t e = cudaGetDevice(&device); e != cudaSuccess) return e;
     const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
-#endif
     const size_t epilogue = sizeof(float4)*J*VR_THREADS + size_t(VR_GROUPS*J)*VR_COLS*3;   // stash + rgb24 staging
-    if (!configured) {
-        size_t most = size_t(VR_TEXEL_BYTES)*VR_WIN_W*VR_MAX_H + table;
+    if (device >= 64 || !configured[device]) {
+        size_t most = size_t(VR_TEXEL_BYTES)*WW*vr_max_h(WW) + table;
         if (most < epilogue) most = epilogue;
-        cudaError_t e = cudaFuncSetAttribute(visualizer_rows_kernel<S, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most));
+        cudaError_t e = cudaFuncSetAttribute(visualizer_rows_kernel<S, J, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (device < 64) configured[device] = true;
     }
-    size_t smem = size_t(VR_TEXEL_BYTES)*VR_WIN_W*size_t(VP.win_h) + table;
+    size_t smem = size_t(VR_TEXEL_BYTES)*WW*size_t(VP.win_h) + table;
     if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
     // frame constants first (same stream): consecutive launches of the process rotate through the slots
     VP.slot = int(g_next_slot.fetch_add(1u) % VR_SLOTS);
     const sfb_uniforms& u = VP.R.u;
     visualizer_frame_consts_kernel<<<1, 32, 0, st>>>(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h), VP.slot);
-    visualizer_rows_kernel<S, J><<<grid, block, smem, st>>>(VP);
+    visualizer_rows_kernel<S, J, WW><<<grid, block, smem, st>>>(VP);
     return cudaSuccess;
 }
 
@@ -722,8 +583,9 @@ template <int S, int J> static cudaError_t launch_rows(VisRowsParams& VP, cudaSt
 // Launch planning, pure host code: which variant (J fragment rows per thread) shades this frame and how many
 // window rows it stages; J = 0 when the frame does not qualify (the tiled kernel takes it). The same vis_front
 // the kernel evaluates gives the texel step per fragment.
-static void plan_rows(const RenderParams& P, int* J_out, int* win_h_out) {
+static void plan_rows(const RenderParams& P, int* J_out, int* win_h_out, int* win_w_out = nullptr) {
     *J_out = 0; *win_h_out = 0;
+    if (win_w_out) *win_w_out = 0;
     const sfb_uniforms& u = P.u;
     const int S = P.ssaa;
     if (!(S == 1 || S == 2 || S == 4)) return;
@@ -745,15 +607,19 @@ static void plan_rows(const RenderParams& P, int* J_out, int* win_h_out) {
     const double sy = fabs(double(t01.y) - double(t00.y))/double(P.Hr - 1);
     if (!(sx == sx && sy == sy && scale == scale) || !(sx < 1e6 && sy < 1e6 && scale < 1e6)) return;
     if (t10.y != t00.y || t01.x != t00.x) return;                      // not separable after all
-    int J;
-    if (7.0*sy <= 1.9 && 8 % S == 0) J = 8;
-    else if (3.0*sy <= 1.9 && 4 % S == 0) J = 4;
-    else return;
+    // J fragment rows share the 4 texel rows of a tap: (J - 1) steps + the bilinear footprint must fit in them
+    int J = 0;
+    for (int candidate : {8, 4, 3, 2})
+        if (candidate % S == 0 && double(candidate - 1)*sy <= 1.9) { J = candidate; break; }
+    if (J == 0) return;
     const double reach = double(scale)*1.0001 + 1.0;
-    if ((VR_COLS - 1)*sx + 2.0*reach + 9.0 > double(VR_WIN_W - 1)) return;
+    const double span_x = (VR_COLS - 1)*sx + 2.0*reach + 9.0;
+    const int WW = span_x <= 63.0 ? 64 : 96;
+    if (span_x > double(WW - 1)) return;
     const int win_h = int(ceil((VR_GROUPS*J - 1)*sy + 2.0*reach)) + 11;   // + alignment, neighbours, the last row quad
-    if (win_h > VR_MAX_H) return;
+    if (win_h > vr_max_h(WW)) return;
     *J_out = J; *win_h_out = win_h;
+    if (win_w_out) *win_w_out = WW;
 }
 
 extern "C" int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int background_h,
@@ -769,25 +635,29 @@ extern "C" int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_
     return SFB_OK;
 }
 
-int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched) {
+int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched, int screen_alpha) {
     *launched = 0;
     static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
     if (disabled) return SFB_OK;
-    int J = 0, win_h = 0;
-    plan_rows(P, &J, &win_h);
+    int J = 0, win_h = 0, WW = 0;
+    plan_rows(P, &J, &win_h, &WW);
     if (J == 0) return SFB_OK;
     const int S = P.ssaa;
     if (int e = build_rows_tables()) return e;
     VisRowsParams VP;
-    VP.R = P; VP.win_h = win_h;
+    VP.R = P; VP.win_h = win_h; VP.screen_alpha = screen_alpha;
     static const int debug = getenv("SFB_ROWS_DEBUG") ? atoi(getenv("SFB_ROWS_DEBUG")) : 0;
     VP.debug = debug;
-    cudaError_t e = cudaSuccess;
-    if (J == 8) {
-        if (S == 1) e = launch_rows<1, 8>(VP, stream); else if (S == 2) e = launch_rows<2, 8>(VP, stream); else e = launch_rows<4, 8>(VP, stream);
-    } else {
-        if (S == 1) e = launch_rows<1, 4>(VP, stream); else if (S == 2) e = launch_rows<2, 4>(VP, stream); else e = launch_rows<4, 4>(VP, stream);
-    }
+    cudaError_t e = cudaErrorInvalidValue;
+    #define SFB_ROWS_CASE(s_, j_, w_) if (S == s_ && J == j_ && WW == w_) e = launch_rows<s_, j_, w_>(VP, stream);
+    // small texel step per fragment (supersampled exports): 64-texel windows
+    SFB_ROWS_CASE(1, 8, 64) SFB_ROWS_CASE(2, 8, 64) SFB_ROWS_CASE(4, 8, 64)
+    SFB_ROWS_CASE(1, 4, 64) SFB_ROWS_CASE(2, 4, 64) SFB_ROWS_CASE(4, 4, 64)
+    // up to ~1 texel per fragment (ssaa 1 or 2 at the background's own resolution): 96-texel windows, fewer rows per thread
+    SFB_ROWS_CASE(1, 4, 96) SFB_ROWS_CASE(1, 3, 96) SFB_ROWS_CASE(1, 2, 96)
+    SFB_ROWS_CASE(2, 4, 96) SFB_ROWS_CASE(2, 2, 96)
+    #undef SFB_ROWS_CASE
+    if (e == cudaErrorInvalidValue) return SFB_OK;                 // no variant for this (S, J, WW): the tiled kernel takes it
     SFB_CUDA(e);
     *launched = 2;                                                 // frame constants + the frame
     return SFB_OK;

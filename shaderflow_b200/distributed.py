@@ -1,11 +1,17 @@
 """Frame-sharded export across the GPUs of one box.
 
-The reference has no multi-GPU path. Here an export shards over TIME: rank r owns the contiguous frame
-range `shard_range(n_frames, r, world)`, computes the (cheap) audio track for the whole clip so every
-recurrence has exactly the reference's state, shades only its own frames into HBM, and rank 0
-reassembles the stream in time order for the sink. The only exchange step is that reassembly, so the
-only collective is point-to-point sends of finished frames to rank 0 (NCCL over NVLink on GPUs; the same
-code runs over gloo on CPU tensors for the host-logic tests)."""
+The reference has no multi-GPU path. Here an export shards over TIME: every rank computes the (cheap) audio
+track for the whole clip so every recurrence has exactly the reference's state, shades only the frames it owns,
+and the stream is reassembled in time order. The only exchange step of the path is that reassembly:
+
+  * frames bound for a SINK (ffmpeg, a file, the null sink) are reassembled in HOST memory: ownership is
+    block-cyclic (`block_owner`), every rank copies its frames device → host over its own PCIe link into its ring
+    of one shared-memory segment, rank 0's writer thread streams them in time order (`negotiate_shared_sink`,
+    csrc/sink.cu). No collective touches the data path; barriers bracket the export.
+  * frames that STAY IN HBM for a consumer on rank 0 (`on_frame`, bench.py's `value` leg) use contiguous ranges
+    (`shard_range`) and are reassembled in rank 0's HBM: peer stores over NVLink from the shading kernel itself
+    (`PeerFrames`, CUDA IPC), or point-to-point NCCL sends when IPC is refused (`FrameGather`; the same code
+    runs over gloo on CPU tensors for the host-logic tests)."""
 from __future__ import annotations
 
 import os
@@ -27,6 +33,11 @@ def owner_of(frame: int, n_frames: int, world: int) -> int:
     base, extra = divmod(n_frames, world)
     edge = extra*(base + 1)
     return frame//(base + 1) if frame < edge else extra + (frame - edge)//max(base, 1)
+
+
+def block_owner(frame: int, block: int, world: int) -> int:
+    """Block-cyclic ownership of the sink-bound sharded export (csrc/sink.cu): frame g → rank (g / block) % world"""
+    return (frame//block) % world
 
 
 def env_rank_world() -> tuple[int, int, int]:
@@ -223,15 +234,17 @@ class PeerFrames:
             ok = 0
         elif rank != 0:
             try:
+                import inspect
                 rebuild, args = payload[0]
                 args = list(args)
-                owner = args[6]                            # device index of the exporting rank
+                where = list(inspect.signature(rebuild).parameters).index("storage_device")
+                owner = args[where]                        # device index of the exporting rank
                 if owner != device and enable_peer is not None:
                     enable_peer(owner)                     # kernels on `device` may store into `owner`'s memory
                 if not os.environ.get("SFB_PEER_OPEN_ON_OWNER"):
                     # map the allocation into THIS rank's device address space (cudaIpcOpenMemHandle maps into
                     # the current device and enables peer access lazily); the tensor only serves as a pointer
-                    args[6] = device
+                    args[where] = device
                 frames = rebuild(*args)                    # a view of rank 0's memory in this process
             except Exception:
                 frames, ok = None, 0
@@ -240,6 +253,43 @@ class PeerFrames:
         if int(flag.item()) == 0:
             return None
         return PeerFrames(frames, first_remote)
+
+
+def negotiate_shared_sink(ctx, frame_bytes: int, rank: int, world: int, slots: int, device=None, group=None):
+    """Collective: rank 0 creates the shared-memory segment of the sharded export's host rings, every other rank
+    attaches to it (csrc/sink.cu). Returns this rank's `SharedSink`, or None on EVERY rank when any rank failed
+    (no memfd/shm, pinning refused) — the export then falls back to staging in rank 0's HBM.
+    ctx None = host-only sinks (CPU tests of the protocol)."""
+    import torch.distributed as dist
+    from shaderflow_b200 import _native as N
+    sink, payload = None, [None]
+    if rank == 0:
+        try:
+            sink = N.SharedSink(ctx, None, 0, world, slots, frame_bytes)
+            payload = [sink.path]
+        except Exception as error:                              # noqa: BLE001 — reported below, collectively
+            payload = [None]
+            _last_error[0] = str(error)
+    dist.broadcast_object_list(payload, src=0, group=group)
+    ok = 1
+    if payload[0] is None:
+        ok = 0
+    elif rank != 0:
+        try:
+            sink = N.SharedSink(ctx, payload[0], rank, world, slots, frame_bytes)
+        except Exception as error:                              # noqa: BLE001
+            ok, _last_error[0] = 0, str(error)
+    on = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    flag = torch.tensor([ok], dtype=torch.int32, device=on)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        if sink is not None:
+            sink.close()
+        return None
+    return sink
+
+
+_last_error = [None]
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -114,7 +114,9 @@ class ExportingHelper:
         command += ["-f", "matroska", "-"] if self.pipe_output else [str(self.output)]
         return command
 
-    def popen(self) -> None:
+    def open_fd(self) -> int:
+        """Opens what the frames are written to (ffmpeg child / file / temporary file) → its descriptor, -1 for
+        the null sink. The sharded export's writer (csrc/sink.cu) takes the descriptor as is."""
         fd = -1
         if self.type is OutputType.RAW:
             self._file = open(self.output, "wb")
@@ -134,6 +136,38 @@ class ExportingHelper:
                                                 stdout=self.stdout, stderr=self.stderr)
                 fd = self.process.stdin.fileno()
         self.fileno = fd
+        return fd
+
+    def check_process(self) -> None:
+        if self.process is not None and self.process.poll() is not None:
+            self.stderr.seek(0)
+            raise RuntimeError("FFmpeg process closed unexpectedly with traceback:\n" + self.stderr.read().decode("utf-8"))
+
+    def abort(self) -> None:
+        """An export that failed half way: no child process, no acquired ring slot and no open file may survive"""
+        if self.process is not None:
+            try:
+                self.process.stdin.close()
+            except Exception:
+                pass
+            self.process.kill()
+            self.process.wait()
+            self.process = None
+        if self._file is not None:
+            try: self._file.close()
+            except Exception: pass
+            self._file = None
+        ring = getattr(self.scene, "_sink_ring", None)
+        if ring is not None:                         # its `acquired` flag / in-flight frames are unknown: drop it
+            self.scene._sink_ring = None
+            try: ring.close()
+            except Exception: pass
+        self.pipe_handle, self._target = None, None
+        if self.bar is not None:
+            self.bar.close()
+
+    def popen(self) -> None:
+        fd = self.open_fd()
         # one ring per scene serves consecutive exports: creating pinned buffers, a stream and a thread per
         # main() call is measurable on short exports
         buffers = max(2, int(self.buffers))
@@ -163,9 +197,7 @@ class ExportingHelper:
         """Hands the frame just rendered to the sink (exporting.py:151-174)"""
         if self.pipe_handle is None:
             return
-        if self.process is not None and self.process.poll() is not None:
-            self.stderr.seek(0)
-            raise RuntimeError("FFmpeg process closed unexpectedly with traceback:\n" + self.stderr.read().decode("utf-8"))
+        self.check_process()
         self.pipe_handle.submit(self._target)
         self._target = None
         if not turbo:

@@ -59,10 +59,13 @@ class ShaderPiano(ShaderModule):
     note_range_dynamics: DynamicNumber = Factory(lambda: DynamicNumber(
         value=np.zeros(2, dtype=np.float32), frequency=0.05, zeta=1/(2**0.5), response=0))
 
-    tree: dict = Factory(dict)
-    """{pitch: {integer second: deque of PianoNote}} — kept for API parity (`notes_between`)"""
     _order: list = Factory(list)
-    """Notes in add_note order: the insertion index is part of the reference's iteration order"""
+    """Every note in add_note order. The insertion index is part of the reference's iteration order (its
+    dict-of-dict-of-deque tree, module.py:103-116, yields a pitch's notes by integer-second bucket, then by
+    insertion): the GPU producer sorts on (pitch, bucket, insertion) and so does `notes_between` below —
+    one flat list is the whole container."""
+    _by_pitch: dict = Factory(dict)
+    """pitch → indices into `_order`, built lazily for the host-side queries"""
     _device: Any = None
     _tracks: Any = None
 
@@ -77,58 +80,71 @@ class ShaderPiano(ShaderModule):
         self.roll_texture    = ShaderTexture(scene=self.scene, name=f"{self.name}Roll").from_numpy(self._empty_roll())
         self.tempo_texture   = ShaderTexture(scene=self.scene, name=f"{self.name}Tempo").from_numpy(np.zeros((100, 1, 2), np.float32))
 
+    def setup(self):
+        # a new export: fps, speed or the notes themselves may have changed since the tracks were computed
+        self._tracks = None
+
     def _empty_keys(self) -> np.ndarray:
         return np.zeros((1, MAX_NOTE), dtype=np.float32)
 
     def _empty_roll(self) -> np.ndarray:
         return np.zeros((MAX_NOTE, MAX_ROLLING, 4), dtype=np.float32)
 
-    # -- data structure (module.py:103-169) ----------------------------------------------------------
-    @staticmethod
-    def _ranges(start: float, end: float) -> Iterable[int]:
-        return range(int(start), int(end) + 1)
+    # -- the score ----------------------------------------------------------------------------------
+    def _invalidate(self) -> None:
+        self._by_pitch.clear()
+        self._device = self._tracks = None
 
     def clear(self):
-        self.tree.clear()
         self._order.clear()
-        self._device = self._tracks = None
+        self.global_minimum_note, self.global_maximum_note = MAX_NOTE, 0
+        self._invalidate()
 
     def add_note(self, note: Optional[PianoNote]) -> None:
         if note is None:
             return
-        for index in self._ranges(note.start, note.end):
-            self.tree.setdefault(note.note, dict()).setdefault(index, deque()).append(note)
         self._order.append(note)
-        self._device = self._tracks = None
-        self.update_global_ranges(note.note)
+        self.global_minimum_note = min(self.global_minimum_note, note.note)
+        self.global_maximum_note = max(self.global_maximum_note, note.note)
+        self._invalidate()
 
     @property
     def notes(self) -> Iterable[PianoNote]:
-        for block in self.tree.values():
-            for notes in block.values():
-                yield from notes
+        """Pitch by pitch in first-appearance order, bucket by bucket — a note spanning several integer seconds
+        appears once per second it touches, as in the reference's tree walk (module.py:118-123)"""
+        if not self._by_pitch:
+            for index, note in enumerate(self._order):
+                self._by_pitch.setdefault(note.note, []).append(index)
+        for indices in self._by_pitch.values():
+            spans = [(int(self._order[i].start), int(self._order[i].end), i) for i in indices]
+            seconds: dict = {}                        # integer seconds of this pitch in first-touched order
+            for lo, hi, _ in spans:
+                for second in range(lo, hi + 1):
+                    seconds.setdefault(second)
+            for second in seconds:
+                yield from (self._order[i] for lo, hi, i in spans if lo <= second <= hi)
+
+    def __iter__(self) -> Iterable[PianoNote]:
+        return self.notes
 
     @property
     def duration(self) -> float:
         return max((note.end for note in self._order), default=0)
 
-    def __iter__(self) -> Iterable[PianoNote]:
-        return self.notes
-
     def notes_between(self, index: int, start: float, end: float) -> Iterable[PianoNote]:
-        exists = set()
-        for other in self._ranges(start, end):
-            for note in self.tree.get(index, dict()).get(other, deque()):
-                if (note.start > end):
-                    continue
-                if (id(note) in exists):
-                    continue
-                exists.add(id(note))
-                yield note
-
-    def update_global_ranges(self, note: int) -> None:
-        self.global_minimum_note = min(self.global_minimum_note, note)
-        self.global_maximum_note = max(self.global_maximum_note, note)
+        """Notes of pitch `index` that touch the integer seconds of [start, end] and have begun by `end`, each
+        once, ordered by the first such second and then by insertion (module.py:131-141)"""
+        if not self._by_pitch:
+            list(self.notes)
+        first, last = int(start), int(end)
+        hits = []
+        for i in self._by_pitch.get(index, ()):
+            note = self._order[i]
+            lo, hi = max(int(note.start), first), min(int(note.end), last)
+            if lo <= hi and not (note.start > end):
+                hits.append((lo, i))
+        for _, i in sorted(hits):
+            yield self._order[i]
 
     @property
     def maximum_velocity(self) -> Optional[int]:
@@ -139,16 +155,12 @@ class ShaderPiano(ShaderModule):
         return min((note.velocity for note in self._order), default=None)
 
     def normalize_velocities(self, minimum: int = 100, maximum: int = 100) -> None:
-        """Literal mirror of module.py:159-169, including that the interpolated value is computed and dropped:
-        every note ends up at the mid velocity"""
-        ma, mi = (self.maximum_velocity, self.minimum_velocity)
-        def new(velocity: int) -> int:
-            if (ma != mi):
-                int((velocity - mi)/(ma - mi)*(maximum - minimum) + minimum)
-            return int((maximum + minimum)/2)
+        """The reference computes an interpolated velocity and drops it (module.py:158-161):
+        every note ends up at the midpoint. Kept, since exports depend on it."""
+        midpoint = int((maximum + minimum)/2)
         for note in self._order:
-            note.velocity = new(note.velocity)
-        self._device = self._tracks = None
+            note.velocity = midpoint
+        self._invalidate()
 
     def load_midi(self, path: Path):
         raise RuntimeError(logger.error(
@@ -205,13 +217,18 @@ class ShaderPiano(ShaderModule):
             rng.next(dt=abs(float(dt[k])))
             ranges[k] = rng.value
         self._tracks = dict(frames=frames, time=time, keys=keys, chan=chan, ranges=ranges,
-                            key=(len(self._order), self.time_offset, self.roll_time, self.lookahead, self.release_before_end))
+                            key=self._tracks_key())
+
+    def _tracks_key(self) -> tuple:
+        scene = self.scene
+        return (len(self._order), self.time_offset, self.roll_time, self.lookahead, self.release_before_end,
+                scene.fps, scene.speed, scene.total_frames)
 
     def update(self):
         scene = self.scene
         if scene.cuda is None:
             return
-        key = (len(self._order), self.time_offset, self.roll_time, self.lookahead, self.release_before_end)
+        key = self._tracks_key()
         if self._tracks is None or self._tracks["frames"] != scene.total_frames or self._tracks["key"] != key:
             self.prepare()
         k = min(scene.frame_index, self._tracks["frames"] - 1)

@@ -68,6 +68,9 @@ class ShaderScene(ShaderModule):
     _peer_frames: Any = None
     """Sharded export: rank 0's staging of the remote frames, mapped into every rank (distributed.PeerFrames)"""
     _peer_frames_key: Any = None
+    _shared_sink: Any = None
+    """Sharded export with a sink: this rank's ring of the shared host segment (distributed.negotiate_shared_sink)"""
+    _shared_sink_key: Any = None
     _updaters: Any = None
     """(len(modules), modules whose update() runs every frame): rebuilt when a module is added"""
     """The frame sink's ring (pinned buffers, copy stream, writer thread), kept across main() calls"""
@@ -85,10 +88,12 @@ class ShaderScene(ShaderModule):
                 try: module.destroy()
                 except Exception: pass
         self._frame_buffer = None
-        ring, self._sink_ring = self._sink_ring, None
-        if ring is not None:
-            try: ring.close()
-            except Exception: pass
+        for attr in ("_sink_ring", "_shared_sink"):
+            ring = getattr(self, attr, None)
+            if ring is not None:
+                try: setattr(self, attr, None); ring.close()
+                except Exception: pass
+        self._peer_frames = None
 
     def initialize(self) -> None:
         if self.shader is not None:
@@ -324,8 +329,10 @@ class ShaderScene(ShaderModule):
         the output path / bytes, or None without `output`. `frames=(a, b)` renders only that range;
         `on_frame(index, device_pointer)` is called after each rendered frame when no sink is open.
         Under torchrun (`torch.distributed` initialised, world > 1; or distributed=True) the export is
-        frame-sharded: this rank shades its contiguous range into HBM and rank 0 reassembles the stream
-        in time order for the sink (distributed.py); other ranks return None."""
+        frame-sharded (distributed.py): with a sink, block-cyclic frames drained by every rank over its own
+        PCIe link into one shared host ring that rank 0's writer streams in time order; without one, contiguous
+        ranges reassembled in rank 0's HBM for `on_frame`. Ranks other than 0 return None. Scenes with GPU
+        feedback (a program texture with temporal > 1: MotionBlur, Life) do not shard — rank 0 exports alone."""
         from shaderflow_b200 import distributed as D
         rank, world = 0, 1
         if distributed is not False:
@@ -334,7 +341,6 @@ class ShaderScene(ShaderModule):
                 rank, world = dist.get_rank(), dist.get_world_size()
             elif distributed:
                 rank, world = D.init_process_group()
-        sharded = world > 1
         self.initialize()
         self.exporting = bool(output)
         self.freewheel = True
@@ -355,37 +361,151 @@ class ShaderScene(ShaderModule):
             if isinstance(module, ShaderProgram) and module.scene_id is None:
                 module.compile()
 
+        # frame k of a feedback scene reads frame k-1's pixels: every frame before it must have been shaded
+        feedback = any(isinstance(m, ShaderProgram) and m.texture.temporal > 1 for m in self.modules)
+        if world > 1 and feedback:
+            logger.info(f"Scene {self.name} has GPU feedback (temporal textures): it does not frame-shard, rank 0 exports alone")
+            if rank != 0:
+                return None
+            world = 1
         export = ExportingHelper(self)
         export.make_buffers(buffers)
+        run = SimpleNamespace(export=export, rank=rank, world=world, on_frame=on_frame, turbo=turbo, frameskip=frameskip,
+                              feedback=feedback, frames=frames, output=output, buffers=buffers)
+        try:
+            if world == 1:
+                self._export_single(run)
+            elif self.exporting:
+                self._export_sharded_sink(run, D)
+            else:
+                self._export_sharded_hbm(run, D)
+        except BaseException:
+            # leave nothing half open: the scene must be able to export again (and ffmpeg must not linger)
+            export.abort()
+            raise
+        finally:
+            self._frame_target, self.render_enabled = None, True
+        result = export.result()
+        export.log_stats(output=result)
+        return result
+
+    def _frame_loop(self, export, last: int, prepare, shaded, frameskip: bool = True) -> None:
+        """Steps frames 0 .. last-1 on the freewheel clock; `prepare(index)` decides before a frame whether it is
+        shaded and where to, `shaded(index)` hands a shaded frame on"""
+        self.vsync = self.scheduler.new(task=self.next, frequency=self.fps, freewheel=True,
+                                        frameskip=frameskip, precise=True)
+        prepare(0)
+        while (task := self.scheduler.next()):           # → self.next(dt): one frame
+            if task is not self.vsync:
+                continue
+            if self.render_enabled:
+                shaded(export.frame)
+            export.update()
+            if self.quit or export.finished or export.frame >= last:
+                break
+            prepare(export.frame)
+
+    def _export_single(self, run) -> None:
+        export = run.export
+        if self.exporting:
+            export.ffmpeg_output(run.output)
+            export.popen()
+        export.open_bar()
+        first, last = run.frames if run.frames is not None else (0, export.total_frames)
+        shade_from = 0 if run.feedback else first            # feedback scenes need their history
+
+        def prepare(index: int) -> None:
+            self.render_enabled = (shade_from <= index < last)
+            sunk = self.exporting and first <= index < last
+            self._frame_target = export.target() if sunk else None
+
+        def shaded(index: int) -> None:
+            if not (first <= index < last):
+                return
+            if self.exporting:
+                export.pipe(turbo=run.turbo)
+            elif run.on_frame is not None:
+                run.on_frame(index, self.frame_pointer)
+
+        self._frame_loop(export, last, prepare, shaded, run.frameskip)
+        export.finish()
+
+    def _export_sharded_sink(self, run, D) -> None:
+        """Sink-bound sharded export: block-cyclic ownership, every rank drains its own frames (csrc/sink.cu)"""
+        import os
+        import torch.distributed as dist
+        export, rank, world = run.export, run.rank, run.world
+        block = max(1, int(os.environ.get("SFB_SHARD_BLOCK", "4")))
+        slots = max(2*block, int(run.buffers), 8)
+        key = (export.frame_bytes, world, slots)
+        if self._shared_sink_key != key:
+            if self._shared_sink is not None:
+                self._shared_sink.close()
+            self._shared_sink = D.negotiate_shared_sink(self.cuda, export.frame_bytes, rank, world, slots, device=f"cuda:{self.device}")
+            self._shared_sink_key = key
+        sink = self._shared_sink
+        if sink is None:                                      # no shared segment on this box: stage in rank 0's HBM
+            return self._export_sharded_hbm(run, D)
+        fd = -1
+        if rank == 0:
+            export.ffmpeg_output(run.output)
+            fd = export.open_fd()
+            export.open_bar()
+        total = export.total_frames
+        try:
+            sink.begin(total, block, fd)
+            dist.barrier()                                    # rank 0 has reset the counters: frames may be produced
+
+            def prepare(index: int) -> None:
+                self.render_enabled = D.block_owner(index, block, world) == rank
+                self._frame_target = sink.acquire() if self.render_enabled else None
+
+            def shaded(index: int) -> None:
+                if rank == 0:
+                    export.check_process()
+                sink.submit()
+
+            self._frame_loop(export, total, prepare, shaded)
+            export.frame = total
+            sink.finish()                                     # this rank's frames have left (rank 0: all written)
+        except BaseException:
+            sink.abort()                                      # unblocks the other ranks with an error
+            self._shared_sink, self._shared_sink_key = None, None
+            sink.close()
+            raise
+        self.cuda.sync()
+        dist.barrier()                                        # the counters may be reset for the next export only now
+        export.finish()
+
+    def _export_sharded_hbm(self, run, D) -> None:
+        """Sharded export whose frames stay in HBM (or whose box has no shared segment): contiguous ranges,
+        reassembled in rank 0's HBM — peer stores over NVLink from the shading kernel (distributed.PeerFrames),
+        else NCCL point-to-point (distributed.FrameGather) — and consumed there in time order"""
+        import torch
+        import torch.distributed as dist
+        export, rank, world, on_frame = run.export, run.rank, run.world, run.on_frame
         if self.exporting and rank == 0:
-            export.ffmpeg_output(output)
+            export.ffmpeg_output(run.output)
             export.popen()
         if rank == 0:
             export.open_bar()
-        first, last = frames if frames is not None else (0, export.total_frames)
-        staging, gather, peer, sent = None, None, None, 0
-        if sharded:
-            # Rank 0 treats its own range like a single-GPU export (frames go straight to the sink ring).
-            # The other ranks shade straight into rank 0's HBM over NVLink when CUDA IPC allows it
-            # (distributed.PeerFrames); otherwise they shade into their own HBM and send each finished block
-            # without waiting, rank 0 having posted the receives before it starts (distributed.FrameGather).
-            import torch
-            first, last = D.shard_range(export.total_frames, rank, world)
-            key = (export.total_frames, self.height, self.width, world)
-            if getattr(self, "_peer_frames_key", None) != key:
-                self._peer_frames = D.PeerFrames.negotiate(export.total_frames, (self.height, self.width, 3), rank, world, self.device,
-                                                              enable_peer=self.cuda.enable_peer)
-                self._peer_frames_key = key
-            peer = self._peer_frames
-            if peer is None:
-                gather = D.FrameGather(export.total_frames, rank, world, chunk=4)
-                if rank == 0:
-                    gather.post((self.height, self.width, 3), torch.uint8, f"cuda:{self.device}")
-                else:
-                    staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
+        first, last = D.shard_range(export.total_frames, rank, world)
+        staging, gather, sent = None, None, 0
+        key = (export.total_frames, self.height, self.width, world)
+        if self._peer_frames_key != key:
+            self._peer_frames = None                          # frees the previous staging before the next is made
+            self._peer_frames = D.PeerFrames.negotiate(export.total_frames, (self.height, self.width, 3), rank, world, self.device,
+                                                       enable_peer=self.cuda.enable_peer)
+            self._peer_frames_key = key
+        peer = self._peer_frames
+        if peer is None:
+            gather = D.FrameGather(export.total_frames, rank, world, chunk=4)
+            if rank == 0:
+                gather.post((self.height, self.width, 3), torch.uint8, f"cuda:{self.device}")
+            else:
+                staging = torch.empty((last - first, self.height, self.width, 3), dtype=torch.uint8, device=f"cuda:{self.device}")
 
         def prepare(index: int) -> None:
-            """Decides, before frame `index` is stepped, whether it is shaded and where to"""
             self.render_enabled = (first <= index < last)
             if peer is not None and rank != 0:
                 self._frame_target = peer.slot(index).data_ptr() if self.render_enabled else None
@@ -394,57 +514,43 @@ class ShaderScene(ShaderModule):
             else:
                 self._frame_target = export.target() if (self.exporting and self.render_enabled) else None
 
-        self.vsync = self.scheduler.new(task=self.next, frequency=self.fps, freewheel=True,
-                                        frameskip=frameskip, precise=True)
-        prepare(0)
-        while (task := self.scheduler.next()):           # → self.next(dt): one frame
-            if task is not self.vsync:
-                continue
-            if self.render_enabled:
-                if peer is not None and rank != 0:
-                    pass                                      # the kernel stored the frame into rank 0's HBM
-                elif staging is not None:
-                    done = export.frame - first + 1            # frames of the shard shaded so far
-                    if done - sent >= gather.chunk or export.frame == last - 1:
-                        gather.send_block(staging[sent:done])
-                        sent = done
-                elif self.exporting:
-                    export.pipe(turbo=turbo)
-                elif on_frame is not None:
-                    on_frame(export.frame, self.frame_pointer)
-            export.update()
-            if self.quit or export.finished or export.frame >= last:
-                break
-            prepare(export.frame)
+        def shaded(index: int) -> None:
+            nonlocal sent
+            if peer is not None and rank != 0:
+                return                                        # the kernel stored the frame into rank 0's HBM
+            if staging is not None:
+                done = index - first + 1                      # frames of the shard shaded so far
+                if done - sent >= gather.chunk or index == last - 1:
+                    gather.send_block(staging[sent:done])
+                    sent = done
+            elif self.exporting:
+                export.pipe(turbo=run.turbo)
+            elif on_frame is not None:
+                on_frame(index, self.frame_pointer)
 
-        if sharded:
-            # the one exchange step of the path: finished frames → rank 0, in time order
-            if peer is not None:
-                import torch.distributed as dist
-                self.cuda.sync()                              # this rank's peer writes have landed
-                dist.barrier()                                # ... and so have everybody's
-            if rank != 0:
-                if gather is not None:
-                    gather.finish()
-            else:
-                index = last
-                blocks = gather.drain() if gather is not None else (peer.frames[a:a + 16] for a in range(0, peer.frames.shape[0], 16))
-                for block in blocks:
-                    for frame in block:
-                        if export.pipe_handle is not None:
-                            export.pipe_handle.submit(frame.data_ptr())     # D2D into the ring, then D2H + write
-                        elif on_frame is not None:
-                            on_frame(index, frame.data_ptr())
-                        index += 1
-            export.frame = export.total_frames
-            self.cuda.sync()
-            if peer is not None:
-                dist.barrier()                                # the staging may be written again only now
+        self._frame_loop(export, last, prepare, shaded)
+        # the one exchange step of the path: finished frames → rank 0, in time order
+        if peer is not None:
+            self.cuda.sync()                                  # this rank's peer writes have landed
+            dist.barrier()                                    # ... and so have everybody's
+        if rank != 0:
+            if gather is not None:
+                gather.finish()
+        else:
+            index = last
+            blocks = gather.drain() if gather is not None else (peer.frames[a:a + 16] for a in range(0, peer.frames.shape[0], 16))
+            for block in blocks:
+                for frame in block:
+                    if export.pipe_handle is not None:
+                        export.pipe_handle.submit(frame.data_ptr())     # D2D into the ring, then D2H + write
+                    elif on_frame is not None:
+                        on_frame(index, frame.data_ptr())
+                    index += 1
+        export.frame = export.total_frames
+        self.cuda.sync()
+        if peer is not None:
+            dist.barrier()                                    # the staging may be written again only now
         export.finish()
-        result = export.result()
-        export.log_stats(output=result)
-        self._frame_target, self.render_enabled = None, True
-        return result
 
     # -- module hooks ------------------------------------------------------------------------------
     def handle(self, message) -> None:

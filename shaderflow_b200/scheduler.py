@@ -1,149 +1,111 @@
-"""Task scheduler. API mirror of shaderflow/scheduler.py; the export path only uses the freewheel
-mode, whose arithmetic (scheduler.py:86-89,152-168) decides every frame's dt and is reproduced exactly
-(it is also what sfb_frame_clock computes in bulk)."""
+"""The export clock. The reference schedules its frame callback on a wall-clock task queue
+(shaderflow/scheduler.py); an offline export only ever uses that queue in FREEWHEEL mode, where time is virtual:
+the k-th call happens "at" the k-th due time and is handed the distance to the previous one. This module is
+that virtual clock and nothing else — there is no sleeping, no wall clock, no frame skipping here, because this
+backend has no realtime mode (scene.py: `realtime` is always False).
+
+What has to match the reference bit for bit is the sequence of `dt` values, since scene time is their running
+sum (scene.py:476-479) and everything downstream (audio read position, dynamics) keys off it. The reference's
+arithmetic (scheduler.py:86-89,152-168), restated:
+
+    due_0 = 0, previous_0 = -1/frequency
+    call k:  dt_k = due_k - previous_k ;  previous_{k+1} = due_k ;  due_{k+1} = due_k (+ period until > due_k)
+
+`sfb_frame_clock` (csrc/core.cu) computes the same sequence in bulk for the audio tracks; tests/test_host.py holds
+both to the goldens produced by the reference's own SchedulerTask.
+
+`scene.scheduler.new(...)`, `.once(...)`, `.next()` and `.clear()` keep their names because example scenes and
+`ShaderScene.main` call them."""
 from __future__ import annotations
 
-import contextlib
 import inspect
-import time
-from collections import deque
-from typing import Any, Callable, Iterable, Optional
-
-from attrs import Factory, define, field
+from typing import Any, Callable, Optional
 
 
-def precise_sleep(seconds: float, *, error: float = 0.001) -> None:
-    start = time.monotonic()
-    if seconds - error > 0:
-        time.sleep(seconds - error)
-    while (time.monotonic() - start) < seconds:
-        pass
+class ClockedTask:
+    """A callback on the virtual clock. `frequency` may be changed between calls (scene.next stores the
+    scene's fps into its own task every frame, scene.py:472-473)."""
 
+    __slots__ = ("task", "args", "kwargs", "frequency", "once", "enabled", "frameskip", "output",
+                 "due", "previous", "_takes_dt", "_order")
 
-@define(eq=False)
-class SchedulerTask:
-    task: Callable
-    args: list = field(factory=list, repr=False)
-    kwargs: dict = field(factory=dict, repr=False)
-    output: Any = field(default=None, repr=False)
-    context: Any = Factory(contextlib.nullcontext)
-    enabled: bool = True
-    once: bool = False
-    frequency: float = 60.0
-    frameskip: bool = True
-    freewheel: bool = False
-    precise: bool = False
-    started: float = Factory(time.monotonic)
-    next_call: Optional[float] = None
-    last_call: Optional[float] = None
-    _dt: bool = False
-
-    def __attrs_post_init__(self):
-        self._dt = "dt" in inspect.signature(self.task).parameters
-        if self.freewheel:
-            self.started = 0
-        self.last_call = (self.last_call or self.started) - self.period
-        self.next_call = (self.next_call or self.started)
-
-    def __hash__(self) -> int:
-        return id(self)
-
-    @property
-    def fps(self) -> float:
-        return self.frequency
-
-    @fps.setter
-    def fps(self, value: float):
-        self.frequency = value
+    def __init__(self, task: Callable, *, frequency: float = 60.0, once: bool = False, frameskip: bool = True,
+                 args: tuple = (), kwargs: Optional[dict] = None, order: int = 0, **_ignored: Any):
+        # `freewheel`, `precise`, `context`, ... of the reference's constructor are accepted and have no meaning here
+        self.task, self.args, self.kwargs = task, tuple(args), dict(kwargs or {})
+        self.frequency, self.once, self.frameskip = float(frequency), bool(once), bool(frameskip)
+        self.enabled, self.output = True, None
+        self.due = 0.0
+        self.previous = 0.0 - self.period
+        self._takes_dt = "dt" in inspect.signature(task).parameters
+        self._order = order
 
     @property
     def period(self) -> float:
         return 1.0/self.frequency
 
-    @period.setter
-    def period(self, value: float):
-        self.frequency = 1/value
+    fps = property(lambda self: self.frequency, lambda self, value: setattr(self, "frequency", float(value)))
 
-    @property
-    def should_delete(self) -> bool:
-        return self.once and not self.enabled
+    def sort_key(self) -> tuple:
+        # one-shot tasks run before periodic ones; then earliest due; then creation order
+        return (0 if self.once else 1, self.due, self._order)
 
-    @property
-    def should_live(self) -> bool:
-        return not self.should_delete
-
-    def __lt__(self, other) -> bool:
-        return True if (self.once and not other.once) else (self.next_call < other.next_call)
-
-    def __gt__(self, other) -> bool:
-        return True if (not self.once and other.once) else (self.next_call > other.next_call)
-
-    def next(self, block: bool = True) -> "SchedulerTask":
-        if not self.freewheel:
-            wait = max(0, self.next_call - time.monotonic())
-            if (not block) and wait > 0:
-                return self
-            (precise_sleep if self.precise else time.sleep)(wait)
-        now = self.next_call if self.freewheel else time.monotonic()
-        if self._dt:
-            self.kwargs["dt"] = now - self.last_call
-            if not self.frameskip:
-                self.kwargs["dt"] = min(self.kwargs["dt"], self.period)
-        self.last_call = now
-        with self.context:
-            self.output = self.task(*self.args, **self.kwargs)
-        while self.next_call <= now:
-            self.next_call += self.period
-        self.enabled = not self.once
+    def fire(self) -> "ClockedTask":
+        now = self.due
+        if self._takes_dt:
+            dt = now - self.previous
+            self.kwargs["dt"] = dt if self.frameskip else min(dt, self.period)
+        self.previous = now
+        self.output = self.task(*self.args, **self.kwargs)
+        if self.once:
+            self.enabled = False
+        else:
+            due = self.due
+            while due <= now:
+                due += self.period
+            self.due = due
         return self
 
 
-@define
 class Scheduler:
-    Task = SchedulerTask
-    tasks: deque = Factory(deque)
+    """Runs whichever enabled task is due first on the virtual clock"""
+    Task = ClockedTask
 
-    def add(self, task: SchedulerTask) -> SchedulerTask:
-        self.tasks.append(task)
-        return task
+    def __init__(self):
+        self.tasks: list[ClockedTask] = []
+        self._created = 0
 
-    def new(self, task: Callable, **options) -> SchedulerTask:
-        return self.add(SchedulerTask(task=task, **options))
+    def _add(self, task: Callable, once: bool, options: dict) -> ClockedTask:
+        self._created += 1
+        entry = ClockedTask(task, once=once, order=self._created, **options)
+        self.tasks.append(entry)
+        return entry
 
-    def once(self, task: Callable, **options) -> SchedulerTask:
-        return self.add(SchedulerTask(task=task, **options, once=True))
+    def new(self, task: Callable, **options) -> ClockedTask:
+        return self._add(task, False, options)
 
-    def delete(self, task: SchedulerTask) -> None:
+    def once(self, task: Callable, **options) -> ClockedTask:
+        return self._add(task, True, options)
+
+    def delete(self, task: ClockedTask) -> None:
         self.tasks.remove(task)
 
     def clear(self) -> None:
         self.tasks.clear()
 
-    @property
-    def enabled_tasks(self) -> Iterable[SchedulerTask]:
-        return (t for t in self.tasks if t.enabled)
-
-    @property
-    def next_task(self) -> Optional[SchedulerTask]:
-        return min(self.enabled_tasks, default=None)
-
-    def _sanitize(self) -> None:
-        alive = [t for t in self.tasks if t.should_live]
-        self.tasks.clear()
-        self.tasks.extend(alive)
-
-    def next(self, block: bool = True) -> Optional[SchedulerTask]:
-        task = self.next_task
-        if task is None:
+    def next(self, block: bool = True) -> Optional[ClockedTask]:
+        ready = [t for t in self.tasks if t.enabled]
+        if not ready:
             return None
-        try:
-            return task.next(block=block)
-        finally:
-            if task.should_delete:
-                self._sanitize()
+        task = min(ready, key=ClockedTask.sort_key).fire()
+        if task.once:
+            self.tasks.remove(task)
+        return task
 
     def all_once(self) -> None:
-        for task in list(self.tasks):
-            if task.once:
-                task.next()
-        self._sanitize()
+        for task in [t for t in self.tasks if t.once]:
+            task.fire()
+            self.tasks.remove(task)
+
+
+SchedulerTask = ClockedTask

@@ -23,19 +23,45 @@ DEFAULT_FRAGMENT = "// sfb200: scene=default"
 FINAL_FRAGMENT = "// sfb200: scene=final"
 
 
+def _field_kinds() -> dict[str, int]:
+    """fixed field → 0 float, -1 int, n > 0 float vector of n"""
+    kinds = {}
+    for name, ctype in N.Uniforms._fields_:
+        if name == "extra":
+            continue
+        length = getattr(ctype, "_length_", 0)
+        kinds[name] = length if length else (-1 if issubclass(ctype, N.c_int32) else 0)
+    return kinds
+
+
+_FIELD_KINDS = _field_kinds()
+
+
+def _scalars(value) -> list:
+    """numpy scalar / array / tuple / number → flat list of Python numbers"""
+    if isinstance(value, (int, float, bool)):
+        return [value]
+    if isinstance(value, np.ndarray):
+        return value.ravel().tolist()
+    if isinstance(value, (tuple, list)):
+        return list(value)
+    return np.asarray(value, dtype=np.float64).ravel().tolist()
+
+
 def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[str]) -> N.Uniforms:
     """name → value table of a pipeline → the POD block; numpy scalars/vectors cast to float32 like
-    GL uniform uploads do"""
-    for name in _FIXED_FIELDS:
-        value = values.get(name)
-        if value is None:
+    GL uniform uploads do (ctypes stores the float32 rounding of the Python float)"""
+    kinds = _FIELD_KINDS
+    for name, value in values.items():
+        kind = kinds.get(name)
+        if kind is None or value is None:
             continue
-        field = getattr(block, name)
-        if hasattr(field, "__len__"):
-            flat = np.asarray(value, dtype=np.float64).reshape(-1)
-            for i in range(len(field)):
-                field[i] = float(flat[i])
-        elif isinstance(field, int):
+        if kind > 0:
+            flat = _scalars(value)
+            field = getattr(block, name)
+            for i in range(kind):
+                field[i] = flat[i]
+        elif kind < 0:
             setattr(block, name, int(value))
         else:
             setattr(block, name, float(value))
@@ -43,9 +69,10 @@ def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[s
         value = values.get(name)
         if value is None:
             raise RuntimeError(f"Uniform '{name}' required by the shader is not in the scene's pipeline")
-        flat = np.asarray(value, dtype=np.float64).reshape(-1)
+        flat = _scalars(value)
+        row = block.extra[slot]
         for i in range(min(4, len(flat))):
-            block.extra[slot][i] = float(flat[i])
+            row[i] = flat[i]
     return block
 
 
@@ -135,6 +162,35 @@ class ShaderProgram(ShaderModule):
         return self
 
     # -- uniforms ------------------------------------------------------------------------------
+    _plan: Any = None
+    """(modules seen, scene id, modules whose pipeline yields a name this program's kernel reads, textures whose
+    boxes it samples): the reference declares a program's uniforms once, at compile() (shader.py:316-317), so
+    WHICH module provides which name is fixed per compilation — only the values change per frame"""
+
+    def gather_planned(self) -> tuple[dict, dict]:
+        """gather(full_pipeline()) restricted to the modules that matter to this program's kernel"""
+        modules = self.scene.modules
+        plan = self._plan
+        if plan is None or plan[0] != len(modules) or plan[1] != self.scene_id:
+            needed = set(_FIELD_KINDS) | set(self.scene_info["extra"])
+            wanted = set(self.scene_info["samplers"])
+            providers, textures = [], []
+            for module in modules:
+                names = {v.name for v in (module.pipeline() or ()) if v.type != "sampler2D"}
+                if names & needed:
+                    providers.append(module)
+                if isinstance(module, ShaderTexture) and (set(module.sampler_names()) & wanted):
+                    textures.append(module)
+            plan = self._plan = (len(modules), self.scene_id, providers, textures)
+        values, samplers = {}, {}
+        for module in plan[2]:
+            for variable in module.pipeline():
+                if variable.value is not None and variable.type != "sampler2D":
+                    values[variable.name] = variable.value
+        for module in plan[3]:
+            samplers.update(module.sampler_names())
+        return values, samplers
+
     def gather(self, pipeline: Iterable[ShaderVariable]) -> tuple[dict, dict]:
         """Splits a pipeline into {uniform name: value} and {sampler name: TextureBox}"""
         values, samplers = {}, {}
@@ -184,7 +240,7 @@ class ShaderProgram(ShaderModule):
             cuda.render_final(pointer, sw, sh, scene.width, scene.height, scene.subsample, 3,
                               target if target is not None else scene.frame_pointer)
             return
-        values, samplers = self.gather(self.full_pipeline())
+        values, samplers = self.gather_planned()
         textures = self.resolve_samplers(samplers)
         # one pass per layer into the newest temporal slot, then the history rolls (shader.py:398-405)
         for layer, box in enumerate(self.texture.row(0)):
@@ -196,7 +252,7 @@ class ShaderProgram(ShaderModule):
 
     def render_fused(self, target: int, ssaa: int) -> None:
         """K3+K4 in one launch straight into `target` (rgb24): iScreen never exists in HBM"""
-        values, samplers = self.gather(self.full_pipeline())
+        values, samplers = self.gather_planned()
         values["iLayer"] = 0
         scene = self.scene
         block, textures = self.uniform_block(values), self.resolve_samplers(samplers)

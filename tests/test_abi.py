@@ -93,7 +93,9 @@ def test_visualizer_launch_plan_is_host_only():
     assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 4)[0] == 8
     assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 3) == (0, 0)         # ssaa 3: tiled kernel
     small = N.Uniforms.defaults(1920, 1080); small.extra[0][0] = 0.8
-    assert N.visualizer_plan(small, (1920, 1080), 1920, 1080, 1) == (0, 0)     # ~0.86 texel per fragment: tiled kernel
+    rows, window = N.visualizer_plan(small, (1920, 1080), 1920, 1080, 1)       # BASELINE configs[1], the reference's default
+    assert rows == 3 and window <= 32                                          # export: ~0.8 texel per fragment, 96-texel windows
+    assert N.visualizer_plan(small, (3840, 2160), 1920, 1080, 1) == (0, 0)     # 1.6 texels per fragment: tiled kernel
     u.iCameraProjection = 2
     assert N.visualizer_plan(u, (1920, 1080), 3840, 2160, 2) == (0, 0)         # equirectangular camera is not separable
     u.iCameraProjection = 0; u.iCameraRight[1] = 0.1

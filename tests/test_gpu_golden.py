@@ -38,6 +38,12 @@ def bind(ctx, case):
     sid = N.scene_lookup(case.scene)
     info = N.scene_info(sid)
     nt = native_textures(ctx, case.tex)
+    # samplers the program declares but this pass never reads (multipass.frag's layer 0 binds iScreen0x0 like the
+    # reference does, shader.py:367-405): a 1x1 placeholder
+    for name in info["samplers"][:info.get("required", len(info["samplers"]))]:
+        if name not in nt:
+            nt[name] = N.Texture(ctx, 1, 1, 4, N.DTYPE_U8, linear=True, repeat_x=False, repeat_y=False)
+            nt[name].write(np.zeros((1, 1, 4), np.uint8))
     samplers = [nt[name] for name in info["samplers"] if name in nt]
     return sid, native_uniforms(case.uniforms, info), samplers, nt
 

@@ -255,6 +255,12 @@ def test_large_frame_properties(ctx, scene_inputs):
     ((240, 135), (258, 146), 2, 1.0, {}),                        # partial tiles right/top, width not a multiple of 4
     ((960, 540), (960, 540), 2, 1.3, dict(iCameraZoom=1.7, iCameraPosition=(0.4, 0.1, 0.0))),   # moved camera: window crosses the wrap
     ((130, 74), (1920, 1080), 2, 2.0, {}),                       # background narrower than the window row: all wrapped loads
+    ((640, 360), (640, 360), 1, 1.2, {}),                        # the reference's default export geometry: ~0.8 texel per
+                                                                 # fragment → 3 rows per thread, 96-texel windows
+    ((640, 360), (320, 180), 2, 2.0, {}),                        # the same step with 2x2 sub-samples: J=2, 96-texel windows
+    ((640, 360), (640, 360), 2, 0.7, {}),                        # 0.4 texel per fragment: J=4
+    ((800, 360), (640, 360), 1, 1.0, {}),                        # background of another aspect ratio
+    ((1920, 1080), (1920, 1080), 1, 1.6, {}),                    # BASELINE configs[1] itself
 ])
 def test_separable_visualizer_kernel_equals_tiled_and_oracle(ctx, bg_size, out, ssaa, volume, camera):
     """visualizer_rows.cu (one thread per fragment column, hinge-weight table) against the per-pixel tiled
@@ -290,8 +296,9 @@ def test_separable_visualizer_kernel_equals_tiled_and_oracle(ctx, bg_size, out, 
 
 @pytest.mark.parametrize("want_aspect", [None, 1.25])
 def test_visualizer_screen_pass_into_rgba8_target(ctx, scene_inputs, want_aspect):
-    """The iScreen pass of an unfused export (sfb_render_target into an RGBA8 texture) runs the tiled kernel with one
-    fragment per thread: same bytes as the generic per-fragment pass, alpha included (0 where the fragment is out of
+    """The iScreen pass of an unfused export (sfb_render_target into an RGBA8 texture) runs the separable kernel with
+    one fragment per "pixel" (the tiled one when the geometry does not qualify): same bytes as the generic
+    per-fragment pass, alpha included (0 where the fragment is out of
     bounds: a wanted aspect narrower than the target's leaves bars on both sides, camera.glsl:86)"""
     from shaderflow_b200 import _native as N
     tex, extra, time = scene_inputs

@@ -38,10 +38,14 @@ def test_piano_module_api_without_gpu():
     ref = P.Piano(P.synthetic_notes(4.0))
     assert (piano.global_minimum_note, piano.global_maximum_note) == (ref.gmin, ref.gmax)
     assert abs(piano.duration - max(n[2] for n in P.synthetic_notes(4.0))) < 1e-12
-    for midi in (60, 61, 62, 70):
-        got = [(n.note, n.start, n.end, n.channel, n.velocity) for n in piano.notes_between(midi, 1.2, 1.2 + piano.lookup_time)]
-        want = [n[:5] for n in ref.notes_between(midi, 1.2, 1.2 + ref.lookup_time)]
-        assert got == want
+    for midi in range(ref.gmin, ref.gmax + 1):
+        for t0 in (0.0, 0.95, 1.2, 2.999, 3.5):
+            got = [(n.note, n.start, n.end, n.channel, n.velocity) for n in piano.notes_between(midi, t0, t0 + piano.lookup_time)]
+            want = [n[:5] for n in ref.notes_between(midi, t0, t0 + ref.lookup_time)]
+            assert got == want, (midi, t0)
+    # iteration order of the whole score = the reference's tree walk (pitch, then integer second, then insertion)
+    walk = [n[:5] for block in ref.tree.values() for notes in block.values() for n in notes]
+    assert [(n.note, n.start, n.end, n.channel, n.velocity) for n in piano] == walk
     names = {v.name: v.value for v in piano.pipeline()}
     assert names["iPianoLimit"] == 256 and names["iPianoRollTime"] == 2 and names["iPianoGlobalMin"] == ref.gmin
     assert [t.name for t in (piano.keys_texture, piano.channel_texture, piano.roll_texture, piano.tempo_texture)] == \
