@@ -120,6 +120,17 @@ int sfb_audio_track(sfb_ctx* ctx, const float* pcm_dev, int64_t n_samples, int c
                     double* scalars_out_dev,
                     float* wave_out_dev, int wave_points, int wave_chunk, int wave_reducer);
 
+/* Audio file ingestion without ffmpeg. The reference decodes files through an ffmpeg child asked
+ * for interleaved float32 (BrokenAudioReader.stream, ffmpeg.py:1279-1330) and transposes every chunk into its host
+ * ring (audio/module.py:449-453). Here the file's own little-endian sample bytes are uploaded as they are and one
+ * kernel converts (libswresample's rules: u8 (x-128)/128, s16 x/2^15, s24 x/2^23, s32 x/2^31, f64 → f32) and
+ * transposes them into the resident planar clip:
+ *   raw_dev     [n_frames][channels] samples of `format`, interleaved, as in a WAV 'data' chunk / decoded FLAC
+ *   planar_dev  [channels][clip_samples] float32; frames land at [offset, offset + n_frames) of every channel */
+enum { SFB_PCM_U8 = 0, SFB_PCM_S16 = 1, SFB_PCM_S24 = 2, SFB_PCM_S32 = 3, SFB_PCM_F32 = 4, SFB_PCM_F64 = 5 };
+int sfb_pcm_ingest(sfb_ctx* ctx, const void* raw_dev, int64_t n_frames, int channels, int format,
+                   float* planar_dev, int64_t clip_samples, int64_t offset);
+
 /* DynamicNumber.next (dynamics.py:197-250) over frames for any float32 vector, in place on
  * values_inout_dev [n_frames][lanes]: row k holds the target of frame k on entry and the state after frame
  * k's update on return. Same kernel as the spectrogram columns of sfb_audio_track. */

@@ -21,6 +21,7 @@ REDUCER = dict(average=0, rms=1, std=2)
 DTYPE_U8, DTYPE_F32, DTYPE_F16 = 0, 1, 2
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
 FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL, RENDER_TILED = 0, 1, 2, 4
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32, PCM_F64 = range(6)
 SCALARS = 5
 SCENE_COUNT = 17
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
@@ -102,6 +103,7 @@ _PROTOTYPES = dict(
     sfb_scene_info_get=(c_int, [c_int, POINTER(SceneInfo)]),
     sfb_render_screen=(c_int, [c_void_p, c_int, POINTER(Uniforms), POINTER(c_void_p), c_int, c_int,
                                c_int, c_int, c_void_p, c_void_p]),
+    sfb_pcm_ingest=(c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int64]),
     sfb_dynamics_scan=(c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(DynamicsParams)]),
     sfb_piano_track=(c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double,
                              c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -440,6 +442,10 @@ class Context:
         arr, n = self._samplers(textures)
         check(lib().sfb_render_frame_probe(self.handle, scene, byref(uniforms), arr, n, flags, width, height, ssaa, subsample,
                                            components, _ptr(dst), _ptr(screen_f32)))
+
+    def pcm_ingest(self, raw, n_frames: int, channels: int, fmt: int, planar, clip_samples: int, offset: int) -> None:
+        """Interleaved file samples (device bytes) → rows [offset, offset+n_frames) of the planar float32 clip"""
+        check(lib().sfb_pcm_ingest(self.handle, _ptr(raw), n_frames, channels, fmt, _ptr(planar), clip_samples, offset))
 
     def destroy(self) -> None:
         if self.handle:

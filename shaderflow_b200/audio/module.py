@@ -36,18 +36,12 @@ class AudioMode(Enum):
 
 
 def read_audio_file(path: Path) -> tuple[np.ndarray, int]:
-    """→ (pcm float32 (channels, samples), samplerate). WAV natively, anything else through ffmpeg"""
+    """→ (pcm float32 (channels, samples), samplerate). RIFF/WAVE natively (audio/reader.py), anything else
+    through ffmpeg when a binary exists"""
     path = Path(path)
-    if path.suffix.lower() == ".wav":
-        from scipy.io import wavfile
-        rate, data = wavfile.read(path)
-        if data.ndim == 1:
-            data = data[:, None]
-        if data.dtype.kind == "i":
-            data = data.astype(np.float32)/float(np.iinfo(data.dtype).max + 1)
-        elif data.dtype.kind == "u":
-            data = (data.astype(np.float32) - 128.0)/128.0
-        return np.ascontiguousarray(data.T.astype(np.float32)), int(rate)
+    if path.suffix.lower() in (".wav", ".wave", ".rf64"):
+        from shaderflow_b200.audio.reader import read_wav
+        return read_wav(path)
     ffmpeg, ffprobe = shutil.which("ffmpeg"), shutil.which("ffprobe")
     if not (ffmpeg and ffprobe):
         raise RuntimeError(f"Decoding '{path}' needs ffmpeg/ffprobe on PATH; load WAV files or call load(pcm, samplerate)")
@@ -85,6 +79,7 @@ class BrokenAudio:
             pcm = pcm[None, :]
         self.clip = np.ascontiguousarray(pcm)
         self.clip_device = None
+        self._wav = None
         self._channels = int(pcm.shape[0])
         if samplerate:
             self._samplerate = samplerate
@@ -92,12 +87,21 @@ class BrokenAudio:
         self.tell = 0
         return self
 
+    _wav: Any = field(default=None, repr=False)
+    """audio/reader.WavInfo of the file the clip came from: the device copy is then made from the file's own sample
+    bytes (pinned staging → H2D → sfb_pcm_ingest) instead of from the host float32 array"""
+
     def device_clip(self, device: int):
         if self.clip is None:
             raise RuntimeError("No audio loaded: set `file=` to an existing file or call load(pcm, samplerate)")
         if self.clip_device is None:
             import torch
-            self.clip_device = torch.from_numpy(self.clip).to(f"cuda:{device}", non_blocking=False)
+            ctx = getattr(getattr(self, "scene", None), "cuda", None)
+            if self._wav is not None and ctx is not None:
+                from shaderflow_b200.audio.reader import upload_wav
+                self.clip_device = upload_wav(ctx, self._wav, device)
+            else:
+                self.clip_device = torch.from_numpy(self.clip).to(f"cuda:{device}", non_blocking=False)
         return self.clip_device
 
     @property
@@ -185,6 +189,9 @@ class BrokenAudio:
             return
         pcm, rate = read_audio_file(self._file)
         self.load(pcm, rate)
+        if self._file.suffix.lower() in (".wav", ".wave", ".rf64"):
+            from shaderflow_b200.audio.reader import parse_wav
+            self._wav = parse_wav(self._file)
 
     stereo = property(lambda self: self.channels == 2)
     mono = property(lambda self: self.channels == 1)

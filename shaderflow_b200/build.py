@@ -19,7 +19,7 @@ PACKAGE = Path(__file__).resolve().parent
 CSRC = PACKAGE/"csrc"
 OBJ = CSRC/"build"
 LIBRARY = PACKAGE/"libsfb200.so"
-UNITS = ("core.cu", "audio.cu", "render.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu")
+UNITS = ("core.cu", "audio.cu", "render.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu", "ingest.cu")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
