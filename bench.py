@@ -6,12 +6,18 @@ export, frame-sharded over N GPUs of one box.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one export of a clip of N seconds through the public API (`ShaderScene.main`): every rank shades
-`--frames-per-step` (60) frames of its contiguous time range with the fused visualizer kernel after the
-STFT/audio-track kernels ran for the clip, and rank 0 reassembles the frames (weak scaling: per-GPU work
-is fixed). Two timed passes share that step:
-  value : inputs (PCM clip, background texture) already resident in HBM, frames stay in HBM;
-  e2e   : the clip comes from pinned HOST memory each step (H2D inside the timed region) and every frame
-          goes through the sink ring to pinned HOST memory (D2H inside the timed region, null sink).
+`--frames-per-step` (60) frames of the clip with the fused visualizer kernel after the STFT/audio-track kernels
+ran for the clip (weak scaling: per-GPU work is fixed). Two timed passes share that step:
+  value : inputs (PCM clip, background texture) already resident in HBM, frames stay in HBM (N > 1: contiguous
+          ranges reassembled in rank 0's HBM by peer stores over NVLink);
+  e2e   : the clip comes from pinned HOST memory each step (H2D inside the timed region) and every frame goes
+          to HOST memory through the sink (D2H inside the timed region, null sink; N > 1: block-cyclic frames,
+          every rank drains its own frames over its own PCIe link into one shared host ring, rank 0's writer
+          streams them in time order).
+The same line carries: `strong` (the full 60 s / 3600-frame clip of BASELINE configs[2] at this N), `verify`
+(N > 1: CRC of a sharded export's frames against a single-GPU render of the same frames), `piano` (configs[4]:
+one 4K PianoRoll export per GPU, concurrently), `stft` (second half of the metric), and at N = 1 `other_configs`
+(configs[1] and configs[3] with their own rooflines and CPU baselines).
 Timing: CUDA events on the launch stream around each step, barrier + synchronize on both sides, max over
 ranks. The oracle (numpy port of the reference path) is only ever the CPU baseline here, never the product.
 """
@@ -51,6 +57,9 @@ def parse_args():
     p.add_argument("--height", type=int, default=2160)
     p.add_argument("--ssaa", type=int, default=2)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-strong", action="store_true", help="skip the 3600-frame strong-scaling leg")
+    p.add_argument("--no-piano", action="store_true", help="skip the configs[4] piano exports")
+    p.add_argument("--no-other", action="store_true", help="skip configs[1] / configs[3] (N = 1)")
     p.add_argument("--hardware-filter", action="store_true", help="SFB_FILTER_HARDWARE instead of the exact sampler")
     return p.parse_args()
 
@@ -205,41 +214,120 @@ def stft_metric(ctx, hbm_peak: float, args) -> dict:
 # -------------------------------------------------------------------------------------------------- #
 # The other single-GPU configurations of BASELINE.json, reported next to the headline (N = 1 only)
 
-def other_configs(local: int) -> dict:
-    """configs[1] (Visualizer, 1080p, reference defaults ssaa=1 subsample=2, white noise) and configs[3]
-    (fractal / ray-march scenes at 7680x4320 with 4x SSAA = 530.8 M shaded fragments per frame) through the
-    public API; CUDA events around scene.main, frames stay in HBM."""
+FP32_PEAK_TFLOPS = 148*128*2*1.965e9/1e12          # nominal: 148 SMs x 128 FP32 lanes x 2 (FMA) x 1.965 GHz = 74.4
+
+
+def ncu_summary() -> dict:
+    try: return json.loads((ROOT/"profiles"/"ncu_summary.json").read_text())
+    except Exception: return {}
+
+
+def timed_export(scene, frames: int, warm: int = 1, reps: int = 2, **flags) -> float:
+    """best-of-`reps` ms of scene.main over `frames` frames, frames staying in HBM, CUDA events"""
     import torch
+    best = float("inf")
+    for i in range(warm + reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(); scene.main(fps=60.0, time=frames/60.0, distributed=False, **flags); b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            best = min(best, a.elapsed_time(b))
+    return best
+
+
+def other_configs(local: int, hbm_peak: float, cpu: bool) -> dict:
+    """configs[1] (Visualizer, 1080p, the reference's defaults ssaa=1 subsample=2, white noise) and configs[3]
+    (fractal / ray-march scenes at 7680x4320 with 4x SSAA = 530.8 M shaded fragments per frame) through the
+    public API; CUDA events around scene.main. Each entry: frames/s with frames staying in HBM, e2e through the
+    null sink, a roofline (HBM bytes as SURVEY §8d defines them; for the ALU-bound fractals also FP32 FLOP/s
+    against the nominal 74 TFLOP/s, FLOPs per launch from the committed ncu capture) and the numpy port's CPU rate."""
     from shaderflow_b200 import synthetic
     from examples import demo
-
-    def run(scene, frames: int, warm: int = 1, reps: int = 2, **flags) -> float:
-        best = float("inf")
-        for i in range(warm + reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record(); scene.main(output=None, fps=60.0, time=frames/60.0, distributed=False, **flags); b.record()
-            torch.cuda.synchronize()
-            if i >= warm:
-                best = min(best, a.elapsed_time(b))
-        return best
-
+    from oracle import cpu_bench
+    prof = ncu_summary()
     out = {}
     demo.Visualizer.background = demo.synthetic_background(1920, 1080)
     scene = demo.Visualizer(device=local); scene.initialize()
-    scene.audio.load(synthetic.noise(2.0), 44100)
-    ms = run(scene, 120, width=1920, height=1080, ssaa=1, subsample=2)
-    out["configs[1] Visualizer 1920x1080 ssaa=1 subsample=2, white noise"] = dict(frames_per_s=120/(ms/1e3), ms_per_frame=ms/120, frames=120)
-    # configs[4]'s scene (8 concurrent exports are 8 independent replicas of this, one per GPU and sink)
-    scene = demo.PianoRoll(device=local); scene.initialize()
-    ms = run(scene, 120, width=3840, height=2160, ssaa=1, subsample=2)
-    out["configs[4] PianoRoll 3840x2160 ssaa=1 subsample=2, one export"] = dict(frames_per_s=120/(ms/1e3), ms_per_frame=ms/120, frames=120)
+    scene.audio.load(synthetic.noise(4.0), 44100)
+    frames = 240
+    flags = dict(width=1920, height=1080, ssaa=1, subsample=2)
+    ms = timed_export(scene, frames, output=None, **flags)
+    ms_e2e = timed_export(scene, frames, output="null", **flags)
+    algorithmic = 1920*1080*3 + 1920*1080*4 + 115*2*4 + 180*2*4                  # rgb24 out + background read once
+    entry = dict(frames_per_s=frames/(ms/1e3), ms_per_frame=ms/frames, frames=frames,
+                 e2e=dict(value=frames/(ms_e2e/1e3), unit="frames/s", d2h_bytes_per_frame=1920*1080*3),
+                 gfragments_per_s=1920*1080*frames/(ms/1e3)/1e9,
+                 kernels="visualizer_rows_kernel<1, 3, 96> (RGBA8 iScreen) + final_kernel (final.glsl, subsample 2): not a box "
+                         "filter at ssaa 1, so the two passes stay separate",
+                 roofline=dict(bound="hbm", achieved=algorithmic*frames/(ms/1e3)/1e9, peak=hbm_peak, unit="GB/s",
+                               frac=algorithmic*frames/(ms/1e3)/1e9/hbm_peak, algorithmic_bytes_per_frame=algorithmic,
+                               note="whole-frame time incl. the host loop, not one kernel; shared-memory / issue bound like the headline kernel"))
+    if cpu:
+        r = cpu_bench.visualizer_sample(width=1920, height=1080, ssaa=1, rows_per_band=8, bands_per_worker=2)
+        entry["cpu_baseline"] = dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+    out["configs[1] Visualizer 1920x1080 ssaa=1 subsample=2, white noise"] = entry
+
     for name, cls in (("Mandelbrot", demo.Mandelbrot), ("Tetration", demo.Tetration), ("RayMarch", demo.RayMarch)):
         scene = cls(device=local); scene.initialize()
-        ms = run(scene, 2, warm=1, reps=1, width=7680, height=4320, ssaa=4, subsample=4)
-        out[f"configs[3] {name} 7680x4320 ssaa=4 (530.8 M fragments/frame)"] = dict(
-            frames_per_s=2/(ms/1e3), ms_per_frame=ms/2, gfragments_per_s=2*530.8416e6/(ms/1e3)/1e9, frames=2)
+        frames = 12
+        flags = dict(width=7680, height=4320, ssaa=4, subsample=4)
+        ms = timed_export(scene, frames, warm=1, reps=2, output=None, **flags)
+        ms_e2e = timed_export(scene, frames, warm=1, reps=1, output="null", **flags)
+        algorithmic = 7680*4320*3
+        per_frame = ms/frames
+        entry = dict(frames_per_s=frames/(ms/1e3), ms_per_frame=per_frame, frames=frames,
+                     e2e=dict(value=frames/(ms_e2e/1e3), unit="frames/s", d2h_bytes_per_frame=algorithmic),
+                     gfragments_per_s=530.8416e6/(per_frame/1e3)/1e9,
+                     kernel=f"frame_lanes_kernel<{name.upper()}, 4> (one lane per sub-sample)",
+                     roofline=dict(bound="hbm", achieved=algorithmic/(per_frame/1e3)/1e9, peak=hbm_peak, unit="GB/s",
+                                   frac=algorithmic/(per_frame/1e3)/1e9/hbm_peak, algorithmic_bytes_per_frame=algorithmic,
+                                   note="ALU/SFU-bound (no texture, 133 MB... 99.5 MB rgb24 per frame): the FP32 rate is the meaningful one"))
+        flops = prof.get(f"frame_lanes_{name.lower()}", {}).get("fp32_flop_per_launch")
+        if flops:
+            tf = flops/(per_frame/1e3)/1e12
+            entry["fp32"] = dict(achieved_tflops=tf, peak_tflops=FP32_PEAK_TFLOPS, frac=tf/FP32_PEAK_TFLOPS,
+                                 flop_per_launch=flops, source="profiles/ncu_summary.json (ncu: FADD + FMUL + 2·FFMA thread instructions)")
+        if cpu:
+            r = cpu_bench.scene_sample(name.lower(), 7680, 4320, 4, rows_per_band=4, bands_per_worker=2)
+            entry["cpu_baseline"] = dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+        out[f"configs[3] {name} 7680x4320 ssaa=4 (530.8 M fragments/frame)"] = entry
     return out
+
+
+def piano_exports(local: int, rank: int, world: int, barrier, D) -> dict:
+    """BASELINE configs[4]: one 4K PianoRoll export per GPU, all at once — independent replicas (each rank has its
+    own score, its own sink ring and its own PCIe link; nothing is exchanged but the statistics gathered here)."""
+    import torch
+    from examples import demo
+    frames = 240
+    demo.PianoRoll.notes = demo.synthetic_notes(frames/60.0 + 2.0, seed=5 + rank)
+    scene = demo.PianoRoll(device=local); scene.initialize()
+    flags = dict(width=3840, height=2160, ssaa=1, subsample=2, fps=60.0, time=frames/60.0, distributed=False)
+    out = {}
+    for leg, output in (("value", None), ("e2e", "null")):
+        scene.main(output=output, **flags)                                     # warm-up
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); scene.main(output=output, **flags); b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        barrier()
+        out[leg] = D.max_over_ranks(ms) if world > 1 else ms
+    stats = [None]*world
+    mine = dict(rank=rank, notes=len(demo.PianoRoll.notes), ms_e2e=out["e2e"])
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_gather_object(stats, mine)
+    else:
+        stats = [mine]
+    demo.PianoRoll.notes = None
+    return dict(workload=f"examples PianoRoll (ShaderPiano + piano.frag), 3840x2160, ssaa=1 subsample=2, {frames} frames per export, "
+                         f"{world} concurrent export(s), one per GPU; BASELINE.json configs[4]",
+                exports=world, frames_per_export=frames,
+                value=world*frames/(out["value"]/1e3), e2e=dict(value=world*frames/(out["e2e"]/1e3), unit="frames/s",
+                d2h_bytes_per_frame=3840*2160*3, sink="one ring and one PCIe link per GPU (null sink)"),
+                unit="frames/s (aggregate)", per_rank=[s_ for s_ in stats if s_ is not None])
 
 
 # -------------------------------------------------------------------------------------------------- #
@@ -318,6 +406,54 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     e2e_ms = [timed(step_e2e) for _ in range(args.steps)]
     clocks_e2e = sampler2.stop() if rank == 0 else {}
 
+    # ---- strong scaling: the whole 60 s / 3600-frame clip of BASELINE configs[2] on these N GPUs --------------
+    strong = None
+    if not args.no_strong:
+        long_clip = synthetic.chirp(60.0)
+        long_pinned = torch.from_numpy(long_clip).pin_memory()
+        long_flags = dict(flags, time=60.0)
+        def strong_value():
+            scene.main(output=None, **long_flags)
+        def strong_e2e():
+            scene.audio.load(long_pinned.numpy(), 44100)
+            scene.main(output="null", buffers=4, **long_flags)
+        scene.audio.load(long_clip, 44100)
+        scene.audio.device_clip(local)
+        strong_value()                                         # untimed: staging for this clip length is negotiated here
+        v_ms = timed(strong_value)
+        strong_e2e()
+        e_ms = timed(strong_e2e)
+        strong = dict(frames=3600, clip_seconds=60.0, value=3600/(v_ms/1e3), e2e=3600/(e_ms/1e3), unit="frames/s",
+                      ms_value=v_ms, ms_e2e=e_ms, scaling="strong: total work fixed at 3600 frames whatever N",
+                      note="every rank steps the host state of all 3600 frames and shades the ones it owns")
+        scene.audio.load(clip, 44100)
+
+    # ---- N > 1: the sharded stream against a single-GPU render of the same frames ----------------------------
+    verify = None
+    if world > 1:
+        import zlib
+        block = int(os.environ.get("SFB_SHARD_BLOCK", "4"))
+        n = world*block + 3                                     # every rank owns a block, plus a partial trailing block
+        vflags = dict(flags, time=n/fps)
+        scene.audio.load(clip[:, :int(n/fps*44100) + 1], 44100)
+        sharded = scene.main(output=bytes, **vflags)
+        if rank == 0:
+            single = scene.main(output=bytes, distributed=False, **vflags)
+            fb = W*H*3
+            crc_a = [zlib.crc32(sharded[k*fb:(k + 1)*fb]) for k in range(len(sharded)//fb)]
+            crc_b = [zlib.crc32(single[k*fb:(k + 1)*fb]) for k in range(len(single)//fb)]
+            verify = dict(frames=n, frames_identical=int(sum(a == b for a, b in zip(crc_a, crc_b))),
+                          bytes_sharded=len(sharded), bytes_single=len(single), ok=bool(crc_a == crc_b and len(crc_a) == n),
+                          crc32_of_frame_crcs=zlib.crc32(np.asarray(crc_a, np.uint32).tobytes()),
+                          how="crc32 of every rgb24 frame of a sharded export (block-cyclic, shared host ring) vs the same "
+                              "frames rendered by rank 0 alone")
+            del sharded, single
+        barrier()
+        scene.audio.load(clip, 44100)
+
+    # ---- BASELINE configs[4]: one PianoRoll export per GPU, concurrently ----------------------------------------
+    piano = None if args.no_piano else piano_exports(local, rank, world, barrier, D)
+
     if rank != 0:
         return
     ms_per_step = float(np.mean(value_ms))
@@ -351,8 +487,11 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, ms_each_step=[round(float(m), 2) for m in value_ms], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=WORKLOAD, frames_per_step_per_gpu=F, global_frames_per_step=total_frames,
-                            parallelism=(f"frame-shard x{world}: contiguous ranges, ranks shade straight into rank 0's HBM over NVLink "
-                                         "(CUDA IPC peer writes), NCCL barrier, rank 0 feeds the sink") if world > 1 else "single GPU",
+                            parallelism=(f"frame-shard x{world}. value: contiguous ranges, ranks shade straight into rank 0's HBM over "
+                                         "NVLink (CUDA IPC peer stores), NCCL barrier. e2e: block-cyclic blocks of "
+                                         f"{os.environ.get('SFB_SHARD_BLOCK', '4')} frames, every rank copies its frames D2H over its own PCIe "
+                                         "link into its ring of one shared host segment, rank 0's writer streams them in time order "
+                                         "(csrc/sink.cu); barriers only") if world > 1 else "single GPU",
                             filter="hardware" if args.hardware_filter else "exact",
                             l2="each step streams %.2f GB of frames per GPU (>> 126 MB L2); the 8.3 MB background is reused "
                                "across frames by design" % (F*W*H*3/1e9)),
@@ -361,15 +500,17 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
                          d2h_bytes_per_step=int(total_frames*W*H*3), ms_per_step=float(np.mean(e2e_ms)),
                          ms_each_step=[round(float(m), 2) for m in e2e_ms], sm_mhz=clocks_e2e.get("sm_mhz"),
                          reasons=clocks_e2e.get("reasons", [])),
-                gpu_launches=int(launches), roofline=roofline, stft=stft)
-    if world == 1:
-        line["other_configs"] = other_configs(local)
+                gpu_launches=int(launches), roofline=roofline, stft=stft, strong=strong, verify=verify, piano=piano)
+    if world == 1 and not args.no_other:
+        line["other_configs"] = other_configs(local, peak, cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args)
         from oracle import cpu_bench
         r = cpu_bench.stft_sample()
         line["stft"]["cpu_baseline"] = dict(value=r["msamples_per_s"], unit="Msamples/s", cores=1, kind="port",
-                                            sample=f"{r['frames']} frames of the numpy STFT -> filterbank -> dynamics port, one thread, {r['seconds']:.2f} s")
+                                            sample=f"{r['frames']} frames of the numpy STFT -> filterbank -> dynamics port (oracle/audio_np.py, "
+                                                   f"pinned bit-exact to the reference's own numpy code by tests/golden; the reference itself "
+                                                   f"is not on this box), one thread as the reference package sets OMP_NUM_THREADS=1, {r['seconds']:.2f} s")
     print(json.dumps(line), file=RESULT, flush=True)
 
 

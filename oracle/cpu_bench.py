@@ -48,9 +48,44 @@ def _band(args) -> int:
     row0, rows = args
     G = _STATE["G"]
     f = G.varyings(_STATE["u"], _STATE["Wr"], _STATE["Hr"], rows=slice(row0, row0 + rows))
-    out = G.frag_visualizer(_STATE["u"], f, _STATE["tex"])
-    G.to_unorm8(out)
+    out = G.SCENES[_STATE.get("scene", "visualizer")](_STATE["u"], f, _STATE["tex"])
+    q = G.to_unorm8(out)
+    s = int(_STATE["u"].iSSAA)
+    if s >= 1 and rows % s == 0 and q.shape[1] % s == 0:
+        # final.glsl where it is a box filter: mean of the s x s quantised sub-samples, 8-bit store
+        box = q.reshape(rows//s, s, q.shape[1]//s, s, 4).astype(np.float32).mean(axis=(1, 3))/np.float32(255)
+        G.to_unorm8(box[..., :3])
     return out.shape[0]*out.shape[1]
+
+
+def _init_scene(scene, width, height, ssaa):
+    from oracle import glsl_np as G
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    u = G.Uniforms(iResolution=(width, height), iWantAspect=width/height, iSSAA=float(ssaa))
+    _STATE.update(G=G, tex={}, u=u, Wr=width*ssaa, Hr=height*ssaa, scene=scene, audio_per_frame=0.0)
+
+
+def scene_sample(scene: str, width: int, height: int, ssaa: int, rows_per_band: int = 1, bands_per_worker: int = 1,
+                 workers: int | None = None) -> dict:
+    """The numpy port of a texture-less scene (mandelbrot / tetration / raymarch) on row bands spread over the
+    target, one band at a time per worker process → frames/s extrapolated from fragments per second"""
+    import multiprocessing as mp
+    workers = workers or usable_cores()
+    Hr = height*ssaa
+    n_bands = workers*bands_per_worker
+    stride = max(rows_per_band, (Hr - rows_per_band)//max(1, n_bands - 1))
+    tasks = [(min(i*stride, Hr - rows_per_band), rows_per_band) for i in range(n_bands)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers, initializer=_init_scene, initargs=(scene, width, height, ssaa)) as pool:
+        pool.map(_band, [(0, 1)]*workers)                   # warm-up: imports, first touch
+        t0 = time.perf_counter()
+        counts = pool.map(_band, tasks, chunksize=1)
+        seconds = time.perf_counter() - t0
+    fragments = int(sum(counts))
+    per_frame = seconds*(width*ssaa*height*ssaa)/fragments
+    return dict(frames_per_s=1.0/per_frame, fragments=fragments, seconds=seconds, cores=workers,
+                sample=f"{n_bands} bands x {rows_per_band} rows of the {width*ssaa}x{height*ssaa} target ({fragments} fragments, "
+                       f"{seconds:.1f} s on {workers} processes), numpy port of the {scene} fragment; 8-bit stores and the box final pass included")
 
 
 def usable_cores() -> int:
@@ -96,7 +131,7 @@ def visualizer_sample(width: int = 3840, height: int = 2160, ssaa: int = 2, rows
                 audio_ms_per_frame=_STATE["audio_per_frame"]*1e3,
                 sample=f"{n_bands} bands x {rows_per_band} rows of the {width*ssaa}x{height*ssaa} iScreen target "
                        f"({fragments} fragments, {seconds:.1f} s on {workers} processes), numpy port of visualizer.frag; "
-                       f"audio track {_STATE['audio_per_frame']*1e3:.2f} ms/frame added; final pass not included")
+                       f"audio track {_STATE['audio_per_frame']*1e3:.2f} ms/frame added; 8-bit stores and the box final pass included")
 
 
 def stft_sample(seconds: float = 20.0) -> dict:

@@ -92,6 +92,59 @@ __global__ void __launch_bounds__(TILE_X*TILE_Y) frame_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused K3+K4 for the ALU-bound scenes (fractals, ray marching): one LANE per shaded sub-sample instead of one
+// thread looping over the S² sub-samples of its pixel. A warp shades a compact block of sub-samples — 32/S²
+// neighbouring output pixels — so lanes that iterate for long (escape-time loops, ray marches) sit next to each
+// other and the warp no longer waits S² times for its slowest lane; the 8-bit box sum is a shuffle reduction.
+// CTA = 8 warps side by side on one output row; the rgb24 segment leaves through shared memory as words.
+
+template <int SCENE, bool HW, int S>
+__global__ void __launch_bounds__(256) frame_lanes_kernel(const __grid_constant__ RenderParams P) {
+    constexpr int SS = S*S, PPW = 32/SS, NPIX = 8*PPW;             // lanes per pixel, pixels per warp, pixels per CTA
+    static_assert(S == 2 || S == 4, "a warp holds whole pixels");
+    __shared__ unsigned int stage[(NPIX*3 + 3)/4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % SS, sx = sub % S, sy = sub / S;
+    const int x = blockIdx.x*NPIX + warp*PPW + lane/SS, y = blockIdx.y;
+    const bool inside = x < P.W;
+    unsigned int r = 0, g = 0, b = 0;
+    if (inside) {
+        const Frag f = make_frag(P, x*S + sx, y*S + sy);
+        const vec4 c = shade<SCENE, HW>(P, f);
+        if (P.dst_f32)
+            reinterpret_cast<float4*>(P.dst_f32)[size_t(y*S + sy)*size_t(P.Wr) + size_t(x*S + sx)] = make_float4(c.x, c.y, c.z, c.w);
+        r = to_unorm8(c.x); g = to_unorm8(c.y); b = to_unorm8(c.z);
+    }
+    #pragma unroll
+    for (int o = 1; o < SS; o <<= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const float inv = 1.0f/float(SS);
+    r = (unsigned int)__float2int_rn(float(r)*inv);
+    g = (unsigned int)__float2int_rn(float(g)*inv);
+    b = (unsigned int)__float2int_rn(float(b)*inv);
+    const bool writer = inside && sub == 0;
+    if (P.comps == 4) {
+        if (writer) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r, g, b, 255);
+        return;
+    }
+    const bool words = (P.W % 4 == 0) && (int(blockIdx.x)*NPIX + NPIX <= P.W);
+    if (!words) {
+        if (writer) { unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r; p[1] = g; p[2] = b; }
+        return;
+    }
+    if (writer) {
+        unsigned char* p = reinterpret_cast<unsigned char*>(stage) + (warp*PPW + lane/SS)*3;
+        p[0] = r; p[1] = g; p[2] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < (NPIX*3)/4) {
+        unsigned int* out = reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(blockIdx.x)*NPIX)*3);
+        out[threadIdx.x] = stage[threadIdx.x];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: fragment/final.glsl:3-33 over an RGBA8 iScreen, LINEAR + CLAMP_TO_EDGE (scene.py:192-193)
 
 struct FinalParams {
@@ -100,49 +153,69 @@ struct FinalParams {
     unsigned char* dst;
 };
 
-SFB_DEV vec3 screen_bilinear(const FinalParams& P, vec2 uv) {
-    float ub = uv.x*float(P.Ws) - 0.5f, vb = uv.y*float(P.Hs) - 0.5f;
-    float fx = floorf(ub), fy = floorf(vb);
-    float a = ub - fx, b = vb - fy;
-    int i0 = int(fx), j0 = int(fy);
-    auto fetch = [&](int i, int j) {
-        i = min(max(i, 0), P.Ws - 1); j = min(max(j, 0), P.Hs - 1);
-        uchar4 c = __ldg(reinterpret_cast<const uchar4*>(P.screen) + size_t(j)*size_t(P.Ws) + size_t(i));
-        return mk3(c.x/255.0f, c.y/255.0f, c.z/255.0f);
-    };
-    vec3 top = fetch(i0, j0)*(1.0f - a) + fetch(i0 + 1, j0)*a;
-    vec3 bot = fetch(i0, j0 + 1)*(1.0f - a) + fetch(i0 + 1, j0 + 1)*a;
-    return top*(1.0f - b) + bot*b;
+// texture(iScreen, uv).rgb scaled by 255: the weights follow the text (frac of u·W − 0.5, clamped texel indices);
+// the unorm8 decode c/255 of the four texels is deferred to ONE multiplication after the taps are summed (a linear
+// map commutes with the filter: the result differs from the literal order of operations by float32 rounding
+// only, ≈ 1e-7, far inside the 8-bit store) — the literal version spent ~60 % of its instructions in 48 IEEE divisions
+SFB_DEV vec3 screen_bilinear255(const FinalParams& P, vec2 uv) {
+    const float ub = uv.x*float(P.Ws) - 0.5f, vb = uv.y*float(P.Hs) - 0.5f;
+    const float fx = floorf(ub), fy = floorf(vb);
+    const float a = ub - fx, b = vb - fy;
+    const int i0 = int(fx), j0 = int(fy);
+    const int ia = min(max(i0, 0), P.Ws - 1), ib = min(max(i0 + 1, 0), P.Ws - 1);
+    const int ja = min(max(j0, 0), P.Hs - 1), jb = min(max(j0 + 1, 0), P.Hs - 1);
+    const uchar4* rowa = reinterpret_cast<const uchar4*>(P.screen) + size_t(ja)*size_t(P.Ws);
+    const uchar4* rowb = reinterpret_cast<const uchar4*>(P.screen) + size_t(jb)*size_t(P.Ws);
+    const uchar4 c00 = __ldg(rowa + ia), c10 = __ldg(rowa + ib), c01 = __ldg(rowb + ia), c11 = __ldg(rowb + ib);
+    const float w11 = a*b, w10 = a - w11, w01 = b - w11, w00 = (1.0f - a) - w01;
+    return mk3(w00*float(c00.x) + w10*float(c10.x) + w01*float(c01.x) + w11*float(c11.x),
+               w00*float(c00.y) + w10*float(c10.y) + w01*float(c01.y) + w11*float(c11.y),
+               w00*float(c00.z) + w10*float(c10.z) + w01*float(c01.z) + w11*float(c11.z));
 }
 
+// Tile = 32 x 8 output pixels; rgb24 rows are staged in shared memory and leave as 32-bit words
 __global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ FinalParams P) {
-    const int x = blockIdx.x*blockDim.x + threadIdx.x;
-    const int y = blockIdx.y*blockDim.y + threadIdx.y;
-    if (x >= P.W || y >= P.H) return;
-    // astuv of the W×H final target (same rasteriser rule as make_frag)
-    const vec2 astuv = mk2(float((double(x) + 0.5)/double(P.W)), float((double(y) + 0.5)/double(P.H)));
-    vec3 rgb;
-    if (P.subsample == 1) {
-        rgb = screen_bilinear(P, astuv);
-    } else {
-        const int kernel = P.subsample;
-        vec3 acc = mk3(0.0f);
-        vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
-        vec2 corner = astuv - (pixel_size/2.0f);
-        vec2 origin = corner + (pixel_size/float(kernel))/2.0f;
-        for (int sx = 0; sx < kernel; sx++)
-            for (int sy = 0; sy < kernel; sy++) {
-                vec2 offset = (pixel_size/float(kernel))*mk2(float(sx), float(sy));
-                acc = acc + screen_bilinear(P, origin + offset);
-            }
-        rgb = acc/float(kernel*kernel);
+    __shared__ unsigned int stage[8][32];
+    const int x = blockIdx.x*32 + threadIdx.x;
+    const int y = blockIdx.y*8 + threadIdx.y;
+    const bool inside = (x < P.W) && (y < P.H);
+    unsigned int r8 = 0, g8 = 0, b8 = 0;
+    if (inside) {
+        // astuv of the W×H final target (same rasteriser rule as make_frag)
+        const vec2 astuv = mk2(float((double(x) + 0.5)/double(P.W)), float((double(y) + 0.5)/double(P.H)));
+        vec3 rgb;
+        if (P.subsample == 1) {
+            rgb = screen_bilinear255(P, astuv)*(1.0f/255.0f);
+        } else {
+            const int kernel = P.subsample;
+            vec3 acc = mk3(0.0f);
+            const vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
+            const vec2 corner = astuv - (pixel_size/2.0f);
+            const vec2 origin = corner + (pixel_size/float(kernel))/2.0f;
+            for (int sx = 0; sx < kernel; sx++)
+                for (int sy = 0; sy < kernel; sy++) {
+                    const vec2 offset = (pixel_size/float(kernel))*mk2(float(sx), float(sy));
+                    acc = acc + screen_bilinear255(P, origin + offset);
+                }
+            rgb = acc*((1.0f/255.0f)/float(kernel*kernel));
+        }
+        r8 = to_unorm8(rgb.x); g8 = to_unorm8(rgb.y); b8 = to_unorm8(rgb.z);
     }
-    const size_t idx = size_t(y)*size_t(P.W) + size_t(x);
     if (P.comps == 4) {
-        reinterpret_cast<uchar4*>(P.dst)[idx] = make_uchar4(to_unorm8(rgb.x), to_unorm8(rgb.y), to_unorm8(rgb.z), 255);
-    } else {
-        unsigned char* p = P.dst + idx*3;
-        p[0] = to_unorm8(rgb.x); p[1] = to_unorm8(rgb.y); p[2] = to_unorm8(rgb.z);
+        if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
+        return;
+    }
+    const bool words = (P.W % 4 == 0) && (int(blockIdx.x)*32 + 32 <= P.W);
+    if (!words) {
+        if (inside) { unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r8; p[1] = g8; p[2] = b8; }
+        return;
+    }
+    unsigned char* row = reinterpret_cast<unsigned char*>(stage[threadIdx.y]);
+    row[threadIdx.x*3 + 0] = r8; row[threadIdx.x*3 + 1] = g8; row[threadIdx.x*3 + 2] = b8;
+    __syncwarp();
+    if (threadIdx.x < 24 && y < P.H) {
+        unsigned int* out = reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(blockIdx.x)*32)*3);
+        out[threadIdx.x] = stage[threadIdx.y][threadIdx.x];
     }
 }
 
@@ -256,6 +329,8 @@ static int fill_params(RenderParams& P, const char* who, int scene, const sfb_un
         SFB_REQUIRE(P.tex[i].lin, "%s: sampler %d has no storage", who, i);
     }
     P.fast = 0;
+    if ((scene == SFB_SCENE_MANDELBROT || scene == SFB_SCENE_TETRATION) && !(flags & SFB_RENDER_LITERAL))
+        P.fast = 1;               // closed-form interior tests / one exp of the combined exponent (scenes.cuh)
     if (scene == SFB_SCENE_VISUALIZER && !(flags & SFB_RENDER_LITERAL)) {
         const DevSampler& bg = P.tex[0];
         if (bg.dtype == SFB_DTYPE_U8 && bg.padded == 4 && bg.filter == SFB_FILTER_LINEAR && bg.w >= 2 && bg.h >= 2
@@ -293,6 +368,11 @@ template <int S, bool HW> struct LaunchFrame {
         frame_kernel<S, HW><<<grid, block, 0, st>>>(P);
     }
 };
+// the ALU-bound scenes at ssaa 2 / 4: one lane per sub-sample
+template <int SCENE, bool HW> static void launch_frame_lanes(const RenderParams& P, cudaStream_t st) {
+    if (P.ssaa == 4) { dim3 grid((P.W + 15)/16, P.H); frame_lanes_kernel<SCENE, HW, 4><<<grid, 256, 0, st>>>(P); }
+    else             { dim3 grid((P.W + 63)/64, P.H); frame_lanes_kernel<SCENE, HW, 2><<<grid, 256, 0, st>>>(P); }
+}
 
 // 2D tensor map over the background's linear mirror, one RGBA8 texel = one uint32 element, box 64x32
 static const CUtensorMap* background_tensor_map(sfb_tex* t) {
@@ -452,7 +532,12 @@ static int render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
         SFB_LAUNCH_CHECK(ctx);
         return SFB_OK;
     }
-    dispatch<LaunchFrame>(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream);
+    const bool lanes = !(flags & SFB_RENDER_LITERAL) && (ssaa == 2 || ssaa == 4) && P.H <= 65535;
+    const bool hw = (flags & SFB_FILTER_HARDWARE) != 0;
+    if (lanes && scene == SFB_SCENE_MANDELBROT)     { hw ? launch_frame_lanes<SFB_SCENE_MANDELBROT, true>(P, ctx->stream) : launch_frame_lanes<SFB_SCENE_MANDELBROT, false>(P, ctx->stream); }
+    else if (lanes && scene == SFB_SCENE_TETRATION) { hw ? launch_frame_lanes<SFB_SCENE_TETRATION, true>(P, ctx->stream) : launch_frame_lanes<SFB_SCENE_TETRATION, false>(P, ctx->stream); }
+    else if (lanes && scene == SFB_SCENE_RAYMARCH)  { hw ? launch_frame_lanes<SFB_SCENE_RAYMARCH, true>(P, ctx->stream) : launch_frame_lanes<SFB_SCENE_RAYMARCH, false>(P, ctx->stream); }
+    else dispatch<LaunchFrame>(scene, hw, P, ctx->stream);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
 }

@@ -220,6 +220,10 @@ SFB_DEV vec4 scene_waveform(const RenderParams& P, const Frag& f) {
 }
 
 // examples/fractals/shaders/mandelbrot.frag:10-31
+// P.fast (every launch but SFB_RENDER_LITERAL): points of the main cardioid and of the period-2 disc never
+// escape, so the loop would run to `quality` and leave iter == quality — the closed-form membership tests
+// (with a 1e-3 safety margin towards the boundary, inside which the loop runs as written) skip those 500
+// iterations for ~90 % of the interior. Same iter, same colour: tests hold the two variants to identical bytes.
 template <bool HW>
 SFB_DEV vec4 scene_mandelbrot(const RenderParams& P, const Frag& f) {
     Camera cam = get_camera(P.u, f);
@@ -228,30 +232,76 @@ SFB_DEV vec4 scene_mandelbrot(const RenderParams& P, const Frag& f) {
     vec2 c = z;
     int quality = int(1000.0f*P.u.iQuality);
     int iter = 0;
-    for (; iter < quality; iter++) {
-        // length(z) > 3.0 without the square root: sqrtf is correctly rounded and monotone, and the float
-        // after 9 already has a root that rounds above 3, so the two tests agree for every dot(z, z)
-        if (dot(z, z) > 9.0f) break;
-        z = mk2(z.x*z.x - z.y*z.y, z.x*z.y + z.y*z.x) + c;
+    bool inside = false;
+    if (P.fast) {
+        const float m = 1.0e-3f;
+        const float px = (c.x - 0.25f)*(1.0f + m), py = c.y*(1.0f + m);          // scaled about the cusp (0.25, 0)
+        const float q = px*px + py*py;
+        const float bx = c.x + 1.0f;
+        inside = (q*(q + px) < 0.25f*py*py) || (bx*bx + c.y*c.y < 0.0625f*(1.0f - m)*(1.0f - m));
+    }
+    if (inside) {
+        iter = quality > 0 ? quality : 0;
+    } else {
+        for (; iter < quality; iter++) {
+            // length(z) > 3.0 without the square root: sqrtf is correctly rounded and monotone, and the float
+            // after 9 already has a root that rounds above 3, so the two tests agree for every dot(z, z)
+            if (dot(z, z) > 9.0f) break;
+            z = mk2(z.x*z.x - z.y*z.y, z.x*z.y + z.y*z.x) + c;
+        }
     }
     float t = powf(1.0f - float(iter)/float(quality), 20.0f);
     return mk4(palette_magma(t), 1.0f);
 }
 
 // examples/fractals/shaders/tetration.frag:28-55
+// The loop is pure issue-bound arithmetic (ncu: 94.7 % issue slots, no divergence: almost every fragment runs all
+// 67 steps), ~98 instructions per step with libdevice powf + expf + logf + cosf + sinf. Two rewrites keep the
+// mathematics and cut the instruction count:
+//   * log(C.r) is loop-invariant (the GLSL recomputes it: same value); cos and sin of one angle come from one
+//     sincosf (the same range reduction and polynomials as cosf / sinf) — every launch;
+//   * P.fast (every launch but SFB_RENDER_LITERAL): pow(C.r, Z.x)·exp(−Z.y·C.t) = exp(Z.x·ln C.r − Z.y·C.t) is ONE
+//     expf of the combined exponent, with ln C.r carried as a float-float pair so that Z.x·ln C.r keeps the
+//     accuracy powf has internally; −Z.y·C.t is rounded to float32 first, exactly as the GLSL's argument of
+//     exp is. One rounding instead of three (pow, exp, their product): within 1-2 ulp of the literal product.
+//     The map is chaotic, so ulp-level differences move isolated pixels — measured on the oracle: 99.7 % of
+//     channels within 1e-3 of the literal evaluation (a 1-ulp perturbation of pow alone gives 99.9 %); the
+//     parity gate for this scene is 97 %.
 template <bool HW>
 SFB_DEV vec4 scene_tetration(const RenderParams& P, const Frag& f) {
     Camera cam = get_camera(P.u, f);
     float Cx = cam.gluv.x, Cy = cam.gluv.y;
     float Cr = sqrtf(Cx*Cx + Cy*Cy), Ct = atan2f(Cy, Cx);
+    const float logCr = logf(Cr);
     float Zx = Cx, Zy = Cy, Zr = Cr;
     const int MAX_STEPS = 67;
     int it = 0;
-    for (it = 0; it < MAX_STEPS; it++) {
-        float r = powf(Cr, Zx)*expf(-Zy*Ct);
-        float t = Zy*logf(Cr) + (Zx*Ct);
-        Zr = r; Zx = r*cosf(t); Zy = r*sinf(t);
-        if (Zr > 100.0f) break;
+    if (P.fast && Cr > 0.0f && Cr < 3.0e38f) {
+        const double L = log(double(Cr));                  // once per fragment
+        const float lh = float(L), ll = float(L - double(lh));
+        for (it = 0; it < MAX_STEPS; it++) {
+            const float e2 = -Zy*Ct;
+            // exponent = Zx*(lh + ll) + e2 as a float-float (hi, lo)
+            const float p = Zx*lh, pe = fmaf(Zx, lh, -p);
+            const float s = p + e2, bb = s - p;
+            const float lo = fmaf(Zx, ll, pe) + ((p - (s - bb)) + (e2 - bb));
+            float r = expf(s);
+            if (r < 3.0e38f) r = fmaf(r, lo, r);           // exp(s + lo) = exp(s)·(1 + lo + ...), |lo| < 1e-5; inf stays inf
+            const float t = Zy*logCr + (Zx*Ct);
+            float sn, cs;
+            sincosf(t, &sn, &cs);
+            Zr = r; Zx = r*cs; Zy = r*sn;
+            if (Zr > 100.0f) break;
+        }
+    } else {
+        for (it = 0; it < MAX_STEPS; it++) {
+            float r = powf(Cr, Zx)*expf(-Zy*Ct);
+            float t = Zy*logCr + (Zx*Ct);
+            float sn, cs;
+            sincosf(t, &sn, &cs);
+            Zr = r; Zx = r*cs; Zy = r*sn;
+            if (Zr > 100.0f) break;
+        }
     }
     float k = float(it/MAX_STEPS);                 // integer division, tetration.frag:50
     float theta = atan2n(Zy, Zx);

@@ -40,7 +40,10 @@ def bind(ctx, case):
     nt = native_textures(ctx, case.tex)
     # samplers the program declares but this pass never reads (multipass.frag's layer 0 binds iScreen0x0 like the
     # reference does, shader.py:367-405): a 1x1 placeholder
-    for name in info["samplers"][:info.get("required", len(info["samplers"]))]:
+    needed = list(info["samplers"][:info.get("required", len(info["samplers"]))])
+    if case.scene == "motionblur":                     # the launcher wants the whole declared history bound
+        needed += [f"iScreen{t}x0" for t in range(int(case.uniforms.extra["iScreenTemporal"]))]
+    for name in needed:
         if name not in nt:
             nt[name] = N.Texture(ctx, 1, 1, 4, N.DTYPE_U8, linear=True, repeat_x=False, repeat_y=False)
             nt[name].write(np.zeros((1, 1, 4), np.uint8))

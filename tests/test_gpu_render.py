@@ -316,3 +316,36 @@ def test_visualizer_screen_pass_into_rgba8_target(ctx, scene_inputs, want_aspect
     assert np.array_equal(got[..., 3], rgba[..., 3])
     if camera:
         assert (got[..., 3] == 0).any() and (got[..., 3] == 255).any()
+
+
+@pytest.mark.parametrize("scene", ["mandelbrot", "tetration", "raymarch"])
+@pytest.mark.parametrize("ssaa,comps", [(2, 3), (4, 3), (4, 4)])
+def test_lane_per_subsample_kernel_equals_the_generic_one(ctx, scene, ssaa, comps):
+    """frame_lanes_kernel (one lane per sub-sample, shuffle box sum; Mandelbrot with the closed-form interior
+    tests) against frame_kernel (one thread per pixel, the literal loop: SFB_RENDER_LITERAL): identical bytes,
+    including partial tiles and a width that is not a multiple of 4"""
+    from shaderflow_b200 import _native as N
+    for Wo, Ho in ((250, 141), (256, 144)):
+        u = N.Uniforms.defaults(Wo, Ho); u.iSSAA = float(ssaa)
+        sid = N.scene_lookup(scene)
+        a = torch.zeros((Ho, Wo, comps), dtype=torch.uint8, device="cuda")
+        b = torch.zeros((Ho, Wo, comps), dtype=torch.uint8, device="cuda")
+        ctx.render_frame(sid, u, [], Wo, Ho, ssaa, ssaa, comps, a)
+        ctx.render_frame(sid, u, [], Wo, Ho, ssaa, ssaa, comps, b, N.RENDER_LITERAL)
+        ctx.sync()
+        assert torch.equal(a, b), (scene, ssaa, (a != b).sum().item())
+
+
+def test_mandelbrot_interior_tests_are_exact_at_8k(ctx):
+    """BASELINE configs[3] geometry (7680x4320, ssaa 4 = 530.8 M fragments): skipping the iteration for points of
+    the main cardioid / period-2 disc must not change a single byte"""
+    from shaderflow_b200 import _native as N
+    Wo, Ho = 7680, 4320
+    u = N.Uniforms.defaults(Wo, Ho); u.iSSAA = 4.0
+    sid = N.scene_lookup("mandelbrot")
+    a = torch.zeros((Ho, Wo, 3), dtype=torch.uint8, device="cuda")
+    b = torch.zeros((Ho, Wo, 3), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(sid, u, [], Wo, Ho, 4, 4, 3, a)
+    ctx.render_frame(sid, u, [], Wo, Ho, 4, 4, 3, b, N.RENDER_LITERAL)
+    ctx.sync()
+    assert torch.equal(a, b), (a != b).sum().item()

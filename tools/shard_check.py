@@ -1,8 +1,14 @@
-"""Under torchrun (N >= 2): a frame-sharded export must produce exactly the bytes of a single-GPU export.
+"""Under torchrun (N >= 2): a frame-sharded export must produce exactly the bytes of a single-GPU export, whichever
+way the frames are reassembled:
+  sink   output=bytes → block-cyclic ownership, every rank drains into the shared host ring (csrc/sink.cu)
+  hbm    output=None, on_frame → contiguous ranges reassembled in rank 0's HBM (peer stores, or NCCL with SFB_NO_PEER_FRAMES=1)
 usage: python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/shard_check.py"""
+import ctypes
 import sys
+import zlib
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
 import torch
 from shaderflow_b200 import distributed as D, synthetic
 from examples.demo import Visualizer, synthetic_background
@@ -13,17 +19,36 @@ D.init_process_group("nccl")
 Visualizer.background = synthetic_background(960, 540)
 scene = Visualizer(device=local)
 scene.initialize()
-seconds = 37/60
+frames = 37
+seconds = frames/60
 scene.audio.load(synthetic.chirp(seconds), 44100)
-flags = dict(width=1280, height=720, ssaa=2, subsample=2, fps=60.0, time=seconds)
-sharded = scene.main(output=bytes, **flags)
+W, H = 1280, 720
+flags = dict(width=W, height=H, ssaa=2, subsample=2, fps=60.0, time=seconds)
+frame_bytes = W*H*3
+cudart = ctypes.CDLL("libcudart.so.12")
+
+
+def crc_of_device(pointer: int) -> int:
+    host = np.empty(frame_bytes, np.uint8)
+    scene.cuda.sync()
+    assert cudart.cudaMemcpy(ctypes.c_void_p(host.ctypes.data), ctypes.c_void_p(pointer), ctypes.c_size_t(frame_bytes), 2) == 0
+    return zlib.crc32(host.tobytes())
+
+
 ok = True
-if rank == 0:
-    single = scene.main(output=bytes, distributed=False, **flags)
-    frame = 1280*720*3
-    same = [sharded[k*frame:(k + 1)*frame] == single[k*frame:(k + 1)*frame] for k in range(len(single)//frame)]
-    ok = len(sharded) == len(single) and all(same)
-    print(f"world {world}: sharded {len(sharded)} bytes, single {len(single)} bytes, identical frames {sum(same)}/{len(same)} -> {'OK' if ok else 'MISMATCH'}")
+for run in range(2):                                   # twice: the rings / staging serve consecutive exports
+    sharded = scene.main(output=bytes, **flags)
+    seen = {}
+    scene.main(output=None, on_frame=lambda index, pointer: seen.__setitem__(index, crc_of_device(pointer)), **flags)
+    if rank == 0:
+        single = scene.main(output=bytes, distributed=False, **flags)
+        want = [zlib.crc32(single[k*frame_bytes:(k + 1)*frame_bytes]) for k in range(frames)]
+        sink = [zlib.crc32(sharded[k*frame_bytes:(k + 1)*frame_bytes]) for k in range(len(sharded)//frame_bytes)]
+        hbm = [seen.get(k) for k in range(frames)]
+        good = (sink == want) and (hbm == want) and len(sharded) == len(single)
+        ok = ok and good
+        print(f"world {world} run {run}: sink {sum(a == b for a, b in zip(sink, want))}/{frames} frames identical, "
+              f"hbm {sum(a == b for a, b in zip(hbm, want))}/{frames} -> {'OK' if good else 'MISMATCH'}", flush=True)
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
 sys.exit(0 if ok else 1)
