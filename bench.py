@@ -249,8 +249,8 @@ def other_configs(local: int, hbm_peak: float, cpu: bool) -> dict:
     out = {}
     demo.Visualizer.background = demo.synthetic_background(1920, 1080)
     scene = demo.Visualizer(device=local); scene.initialize()
-    scene.audio.load(synthetic.noise(4.0), 44100)
-    frames = 240
+    scene.audio.load(synthetic.noise(10.0), 44100)
+    frames = 600                                                    # the reference's default runtime: 10 s (scene.py:226)
     flags = dict(width=1920, height=1080, ssaa=1, subsample=2)
     ms = timed_export(scene, frames, output=None, **flags)
     ms_e2e = timed_export(scene, frames, output="null", **flags)

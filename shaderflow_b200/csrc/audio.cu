@@ -130,13 +130,27 @@ __device__ __forceinline__ void stockham_pass(cpx* buf, const float2* tw, int Ns
     __syncthreads();
 }
 
+// The first radix-16 pass (Ns = 1: no twiddles) with its 16 inputs already in registers: thread `tid` owns points
+// tid + r*N/16 — the windowed samples it loaded itself — and scatters the butterfly's outputs into `buf`.
+template <int LOG2N>
+__device__ __forceinline__ void stockham_first_pass(cpx* buf, cpx (&v)[16], int tid) {
+    constexpr int N = 1 << LOG2N, T = N/16;
+    if (tid < T) {
+        dft16(v);
+        #pragma unroll
+        for (int r = 0; r < 16; r++) buf[pad(tid*16 + r)] = v[r];
+    }
+    __syncthreads();
+}
+
+// Passes 2.. of the transform (the first one is stockham_first_pass)
 template <int LOG2N>
 __device__ __forceinline__ void fft_inplace(cpx* buf, const float2* tw, int tid) {
     using L = TwiddleLayout<LOG2N>;
     constexpr int FULL = LOG2N/4, REM = LOG2N%4;
-    int Ns = 1;
+    int Ns = 16;
     #pragma unroll
-    for (int p = 0; p < FULL; p++) { stockham_pass<LOG2N, 16>(buf, tw + L::offset(p), Ns, tid); Ns *= 16; }
+    for (int p = 1; p < FULL; p++) { stockham_pass<LOG2N, 16>(buf, tw + L::offset(p), Ns, tid); Ns *= 16; }
     if constexpr (REM == 1) stockham_pass<LOG2N, 2>(buf, tw + L::offset(FULL), Ns, tid);
     if constexpr (REM == 2) stockham_pass<LOG2N, 4>(buf, tw + L::offset(FULL), Ns, tid);
     if constexpr (REM == 3) stockham_pass<LOG2N, 8>(buf, tw + L::offset(FULL), Ns, tid);
@@ -171,48 +185,38 @@ stft_mel_kernel(const __grid_constant__ StftParams P) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
     for (int i = tid; i < TW; i += nthreads) tw[i] = P.twiddle[i];
+    // The window coefficients this thread needs are the same for every frame: thread `tid` always owns the
+    // window positions tid + r*N/16 (the inputs of its first butterfly) — 16 registers, loaded once
+    constexpr int T = N/16;
+    float wreg[16];
+    #pragma unroll
+    for (int r = 0; r < 16; r++) wreg[r] = (tid < T) ? __ldg(P.window + tid + r*T) : 0.0f;
 
     for (int frame = blockIdx.x; frame < P.n_frames; frame += gridDim.x) {
-        __syncthreads();
-        // ---- 1. window load: aligned float4 reads, scatter into z = L + iR -------------------
+        // ---- 1. window [tell-N-1, tell-1) of both channels straight from the clip into the first butterfly:
+        //         lane-consecutive (coalesced) loads at stride N/16, window multiply, z = L + iR -------------
         const long long lo = P.tell[frame] - N - 1;
-        for (int c = 0; c < 2; c++) {
-            if (c >= P.channels) {
-                for (int n = tid; n < N; n += nthreads) buf[pad(n)].y = 0.0f;
-                continue;
-            }
-            // x0 = first sample of the window (may point before the clip: guarded below); all indexing
-            // below is 32-bit relative to it
-            const float* x0 = P.pcm + (long long)c*P.n_samples + lo;
-            const int before = (lo < 0) ? int(-lo > N ? N : -lo) : 0;              // window samples before the clip start
-            const long long room = P.n_samples - lo;
-            const int avail = room > N ? N : (room < 0 ? 0 : int(room));          // window samples inside the clip
-            // first offset <= 0 whose address is 16-byte aligned
-            const int mis = int((reinterpret_cast<uintptr_t>(x0) >> 2) & 3);
-            for (int q = 4*tid - mis; q < N; q += 4*nthreads) {
-                float4 s;
-                if (q >= before && q + 3 < avail) {
-                    s = __ldg(reinterpret_cast<const float4*>(x0 + q));
-                } else {
-                    s.x = (q + 0 >= before && q + 0 < avail) ? __ldg(x0 + q + 0) : 0.0f;
-                    s.y = (q + 1 >= before && q + 1 < avail) ? __ldg(x0 + q + 1) : 0.0f;
-                    s.z = (q + 2 >= before && q + 2 < avail) ? __ldg(x0 + q + 2) : 0.0f;
-                    s.w = (q + 3 >= before && q + 3 < avail) ? __ldg(x0 + q + 3) : 0.0f;
-                }
-                const float e[4] = {s.x, s.y, s.z, s.w};
-                #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int n = q + t;
-                    if (n >= 0 && n < N) {
-                        const float w = e[t]*__ldg(P.window + n);
-                        if (c == 0) buf[pad(n)].x = w; else buf[pad(n)].y = w;
-                    }
-                }
+        const int before = (lo < 0) ? int(-lo > N ? N : -lo) : 0;                 // window samples before the clip start
+        const long long room = P.n_samples - lo;
+        const int avail = room > N ? N : (room < 0 ? 0 : int(room));             // window samples inside the clip
+        cpx v[16];
+        if (tid < T) {
+            const float* xl = P.pcm + lo;                                         // may point before the clip: guarded
+            const float* xr = P.pcm + P.n_samples + lo;
+            const bool whole = (before == 0) && (avail == N);
+            #pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int n = tid + r*T;
+                const bool in = whole || (n >= before && n < avail);
+                const float l = in ? __ldg(xl + n) : 0.0f;
+                const float rr = (in && P.channels == 2) ? __ldg(xr + n) : 0.0f;
+                v[r] = cpx{l*wreg[r], rr*wreg[r]};
             }
         }
-        __syncthreads();
+        __syncthreads();                                                          // the previous frame is done with buf
 
         // ---- 2. FFT ------------------------------------------------------------------------
+        stockham_first_pass<LOG2N>(buf, v, tid);
         fft_inplace<LOG2N>(buf, tw, tid);
 
         // ---- 3. split L/R spectra, magnitude (registers), then park in smem -----------------

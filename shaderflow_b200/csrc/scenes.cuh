@@ -281,10 +281,11 @@ SFB_DEV vec4 scene_tetration(const RenderParams& P, const Frag& f) {
         const float lh = float(L), ll = float(L - double(lh));
         for (it = 0; it < MAX_STEPS; it++) {
             const float e2 = -Zy*Ct;
-            // exponent = Zx*(lh + ll) + e2 as a float-float (hi, lo)
-            const float p = Zx*lh, pe = fmaf(Zx, lh, -p);
-            const float s = p + e2, bb = s - p;
-            const float lo = fmaf(Zx, ll, pe) + ((p - (s - bb)) + (e2 - bb));
+            // exponent = Zx*(lh + ll) + e2: s is its float32 rounding (one FMA), lo what the rounding dropped —
+            // e2 - s is exact whenever s and e2 are within a factor 2 (Sterbenz), else its rounding error is
+            // below ulp(s)/2, i.e. no worse than the rounding of the literal product's exponent
+            const float s = fmaf(Zx, lh, e2);
+            const float lo = fmaf(Zx, ll, fmaf(Zx, lh, e2 - s));
             float r = expf(s);
             if (r < 3.0e38f) r = fmaf(r, lo, r);           // exp(s + lo) = exp(s)·(1 + lo + ...), |lo| < 1e-5; inf stays inf
             const float t = Zy*logCr + (Zx*Ct);
