@@ -105,6 +105,9 @@ int sfb_stft_mel(sfb_ctx* ctx, const float* pcm_dev, int64_t n_samples, int chan
  *   (3) waveform reducer rows (audio/waveform.py:14-22,64-87): wave_out_dev [n_frames][points][channels].
  * dt_dev [n_frames] float64 is scene.dt per frame (sfb_frame_clock). Any of spec_inout_dev /
  * scalars_out_dev / wave_out_dev may be NULL to skip that part.
+ * Synchronisation: with wave_out_dev the call reads tell[0] and tell[n_frames-1] back to size its chunk table, i.e. it
+ * blocks until everything enqueued on the ctx stream so far has finished (once per export, not per frame); without
+ * it the call only enqueues.
  */
 enum { SFB_SCALAR_VOLUME = 0, SFB_SCALAR_VOLUME_INTEGRAL = 1, SFB_SCALAR_STD = 2,
        SFB_SCALAR_VOLUME_TARGET = 3, SFB_SCALAR_STD_TARGET = 4, SFB_SCALARS = 5 };

@@ -204,7 +204,7 @@ extern "C" int sfb_tex_destroy(sfb_tex* t) {
     if (t->obj) cudaDestroyTextureObject(t->obj);
     if (t->array) cudaFreeArray(t->array);
     if (t->lin) cudaFree(t->lin);
-    if (t->tmap_dev) cudaFree(t->tmap_dev);
+    for (auto& m : t->tmaps) if (m.dev) cudaFree(m.dev);
     delete t;
     return SFB_OK;
 }

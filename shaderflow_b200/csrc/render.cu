@@ -374,34 +374,41 @@ template <int SCENE, bool HW> static void launch_frame_lanes(const RenderParams&
     else             { dim3 grid((P.W + 63)/64, P.H); frame_lanes_kernel<SCENE, HW, 2><<<grid, 256, 0, st>>>(P); }
 }
 
-// 2D tensor map over the background's linear mirror, one RGBA8 texel = one uint32 element, box 64x32
-static const CUtensorMap* background_tensor_map(sfb_tex* t) {
+// 2D tensor map over the background's linear mirror, one RGBA8 texel = one uint32 element, box box_w x box_h
+// (cached per texture and box shape; the descriptor is copied to device memory once)
+const void* sfb_background_tensor_map(sfb_tex* t, int box_w, int box_h) {
     static const bool disabled = getenv("SFB_NO_TMA") != nullptr;      // debugging knob
     if (disabled) return nullptr;
-    if (t->external || t->dtype != SFB_DTYPE_U8 || t->padded != 4 || (t->w % 4) != 0 || t->w < VT_TMA_W || t->h < VT_TMA_H)
+    if (t->external || t->dtype != SFB_DTYPE_U8 || t->padded != 4 || (t->w % 4) != 0 || t->w < box_w || t->h < box_h
+        || box_w > 256 || box_h > 256)
         return nullptr;
-    if (!t->tmap_tried) {
-        t->tmap_tried = true;
-        static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr; cudaDriverEntryPointQueryResult q;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-                return nullptr;
-            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-        }
-        cuuint64_t dims[2] = {cuuint64_t(t->w), cuuint64_t(t->h)};
-        cuuint64_t strides[1] = {cuuint64_t(t->w)*4};
-        cuuint32_t box[2] = {VT_TMA_W, VT_TMA_H}, estr[2] = {1, 1};
-        CUresult rc = encode(reinterpret_cast<CUtensorMap*>(t->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, t->lin, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        t->tmap_ok = (rc == CUDA_SUCCESS);
-        if (t->tmap_ok) {   // the kernel reads the descriptor from global memory
-            t->tmap_ok = cudaMalloc(&t->tmap_dev, sizeof(CUtensorMap)) == cudaSuccess
-                      && cudaMemcpy(t->tmap_dev, t->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
-        }
+    for (const auto& m : t->tmaps)
+        if (m.box_w == box_w && m.box_h == box_h) return m.dev;
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
-    return t->tmap_ok ? static_cast<const CUtensorMap*>(t->tmap_dev) : nullptr;
+    alignas(64) CUtensorMap map;
+    cuuint64_t dims[2] = {cuuint64_t(t->w), cuuint64_t(t->h)};
+    cuuint64_t strides[1] = {cuuint64_t(t->w)*4};
+    cuuint32_t box[2] = {cuuint32_t(box_w), cuuint32_t(box_h)}, estr[2] = {1, 1};
+    void* dev = nullptr;
+    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, t->lin, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc == CUDA_SUCCESS && (cudaMalloc(&dev, sizeof(CUtensorMap)) != cudaSuccess
+                               || cudaMemcpy(dev, &map, sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess)) {
+        if (dev) cudaFree(dev);
+        dev = nullptr;
+    }
+    t->tmaps.push_back({box_w, box_h, dev});       // a failed encoding is remembered too (dev == NULL)
+    return dev;
+}
+static const CUtensorMap* background_tensor_map(sfb_tex* t) {
+    return static_cast<const CUtensorMap*>(sfb_background_tensor_map(t, VT_TMA_W, VT_TMA_H));
 }
 
 template <int S> static cudaError_t launch_visualizer_tiled(const VisualizerParams& VP, cudaStream_t st) {
@@ -427,7 +434,7 @@ static int visualizer_screen_pass(sfb_ctx* ctx, const RenderParams& P, sfb_tex* 
     VP.R.W = P.Wr; VP.R.H = P.Hr; VP.R.ssaa = 1; VP.R.subsample = 1; VP.R.comps = 4;
     if (!(flags & SFB_RENDER_TILED)) {            // the separable kernel, one fragment per "output pixel", alpha kept
         int launched = 0;
-        if (int e = sfb_visualizer_rows_launch(VP.R, ctx->stream, &launched, 1)) return e;
+        if (int e = sfb_visualizer_rows_launch(VP.R, ctx->stream, &launched, 1, background)) return e;
         if (launched) { ctx->launches += launched - 1; SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
     }
     VP.tmap = background_tensor_map(background);
@@ -512,7 +519,7 @@ static int render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
         // production path of the headline scene: the separable kernel when the camera allows it, ...
         if (!(flags & SFB_RENDER_TILED)) {
             int launched = 0;
-            if (int e = sfb_visualizer_rows_launch(P, ctx->stream, &launched)) return e;
+            if (int e = sfb_visualizer_rows_launch(P, ctx->stream, &launched, 0, samplers[0])) return e;
             if (launched) { ctx->launches += launched - 1; SFB_LAUNCH_CHECK(ctx); return SFB_OK; }
         }
         // ... else one thread per output pixel over a shared-memory window of the background

@@ -56,9 +56,10 @@ struct sfb_tex {
     cudaTextureObject_t obj = 0;
     void* lin = nullptr;
     const void* external = nullptr;
-    bool tmap_tried = false, tmap_ok = false;
-    alignas(64) unsigned char tmap[128] = {};   // CUtensorMap over `lin` (visualizer window loads)
-    void* tmap_dev = nullptr;                   // its device copy
+    // CUtensorMaps over `lin` (2D uint32 views, one per box shape the visualizer kernels stage their windows with);
+    // dev = device copy of the descriptor (the kernels read it from global memory), NULL when encoding failed
+    struct TensorMap { int box_w, box_h; void* dev; };
+    std::vector<TensorMap> tmaps;
     bool array_stale = false;          // rendered into through sfb_tex_storage: cudaArray copy is old
     int w = 0, h = 0, comps = 0, padded = 0, dtype = 0, filter = 0, rx = 1, ry = 1;
     size_t texel_bytes() const { return size_t(padded)*(dtype == SFB_DTYPE_U8 ? 1 : (dtype == SFB_DTYPE_F16 ? 2 : 4)); }

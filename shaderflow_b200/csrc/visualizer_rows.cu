@@ -66,6 +66,7 @@ struct VisRowsParams {
     int slot;                          // g_frame entry written by visualizer_frame_consts_kernel for this frame
     int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
     int screen_alpha;                  // comps == 4: store fragColor.a (iScreen pass of an unfused export) instead of 255
+    const void* tmap;                  // device CUtensorMap of the background with a WW x win_h box, or NULL (bulk row copies)
 };
 
 SFB_DEV void bulk_load_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
@@ -227,14 +228,17 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         if (win[3]) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bar, VR_WIN_W*4*win_h);
+            // ---- B1. TMA: the raw RGBA8 window lands at the start of the window buffer (WW*4 bytes per row) —
+            //          ONE tensor load (cp.async.bulk.tensor.2d, box WW x win_h) when the launcher made a map
+            if (VP.tmap) tma_load_2d(vr_smem, VP.tmap, &bar, x0, y0);
         }
     }
     __syncthreads();
     const int x0 = win[0], y0 = win[1];
     const bool window_ok = win[2] != 0, tma = win[3] != 0;
 
-    // ---- B1. TMA: raw RGBA8 rows land at the start of the window buffer (256 B per row) -------------
-    if (tma && tid < win_h) {
+    // ---- B1'. no tensor map (odd texture widths, SFB_NO_TMA): one bulk copy per window row -----------
+    if (tma && !VP.tmap && tid < win_h) {
         const unsigned int* src = reinterpret_cast<const unsigned int*>(bg.lin) + size_t(y0 + tid)*size_t(bg.w) + size_t(x0);
         bulk_load_row(vr_smem + tid*(VR_WIN_W*4), src, VR_WIN_W*4, &bar);
     }
@@ -635,7 +639,7 @@ extern "C" int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_
     return SFB_OK;
 }
 
-int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched, int screen_alpha) {
+int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* launched, int screen_alpha, sfb_tex* background) {
     *launched = 0;
     static const bool disabled = getenv("SFB_NO_ROWS") != nullptr;     // debugging knob: tiled kernel only
     if (disabled) return SFB_OK;
@@ -646,6 +650,7 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* 
     if (int e = build_rows_tables()) return e;
     VisRowsParams VP;
     VP.R = P; VP.win_h = win_h; VP.screen_alpha = screen_alpha;
+    VP.tmap = background ? sfb_background_tensor_map(background, WW, win_h) : nullptr;
     static const int debug = getenv("SFB_ROWS_DEBUG") ? atoi(getenv("SFB_ROWS_DEBUG")) : 0;
     VP.debug = debug;
     cudaError_t e = cudaErrorInvalidValue;

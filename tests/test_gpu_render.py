@@ -356,3 +356,38 @@ def test_mandelbrot_interior_tests_are_exact_at_8k(ctx):
     ctx.render_frame(sid, u, [], Wo, Ho, 4, 4, 3, b, N.RENDER_LITERAL)
     ctx.sync()
     assert torch.equal(a, b), (a != b).sum().item()
+
+
+def test_float16_textures_sample_and_serve_as_render_targets(ctx):
+    """SFB_DTYPE_F16 (texture.py:28-38 "f2"): upload / read-back identity, exact sampling of half texels, and a pass
+    rendered into a half RGBA target = the float32 pass rounded to half"""
+    from shaderflow_b200 import _native as N
+    rng = np.random.default_rng(4)
+    uv = rng.uniform(-0.3, 1.3, (2000, 2)).astype(np.float32)
+    uv_d = torch.from_numpy(uv).cuda()
+    out_d = torch.zeros((2000, 4), dtype=torch.float32, device="cuda")
+    for comps in (1, 2, 4):
+        data = rng.normal(size=(9, 13, comps)).astype(np.float16)
+        nt = N.Texture(ctx, 13, 9, comps, N.DTYPE_F16)
+        nt.write(data)
+        assert np.array_equal(nt.read()[..., :comps], data)
+        for linear in (False, True):
+            nt.set_sampling(linear, True, False)
+            want = G.Texture(data.astype(np.float32), linear=linear, repeat_x=True, repeat_y=False).sample(uv)
+            nt.sample(uv_d, out_d, N.FILTER_EXACT); ctx.sync()
+            got = out_d.cpu().numpy()
+            if linear:
+                assert np.abs(got - want).max() < 2e-5*max(1.0, np.abs(want).max())
+            else:
+                assert (np.abs(got - want).max(axis=1) < 1e-6).mean() > 0.999
+        nt.destroy()
+    Wt, Ht = 96, 54
+    u = N.Uniforms.defaults(Wt, Ht); u.iTime = 0.8
+    sid = N.scene_lookup("shadertoy")
+    half = N.Texture(ctx, Wt, Ht, 4, N.DTYPE_F16)
+    full = N.Texture(ctx, Wt, Ht, 4, N.DTYPE_F32)
+    ctx.render_target(sid, u, [], half)
+    ctx.render_target(sid, u, [], full)
+    ctx.sync()
+    assert np.array_equal(half.read(), full.read().astype(np.float16))
+    half.destroy(); full.destroy()
