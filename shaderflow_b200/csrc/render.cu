@@ -151,6 +151,7 @@ struct FinalParams {
     const unsigned char* screen; int Ws, Hs;
     int W, H, subsample, comps;
     unsigned char* dst;
+    double inv_W, inv_H;
 };
 
 // texture(iScreen, uv).rgb scaled by 255: the weights follow the text (frac of u·W − 0.5, clamped texel indices);
@@ -164,13 +165,13 @@ SFB_DEV vec3 screen_bilinear255(const FinalParams& P, vec2 uv) {
     const int i0 = int(fx), j0 = int(fy);
     const int ia = min(max(i0, 0), P.Ws - 1), ib = min(max(i0 + 1, 0), P.Ws - 1);
     const int ja = min(max(j0, 0), P.Hs - 1), jb = min(max(j0 + 1, 0), P.Hs - 1);
-    const uchar4* rowa = reinterpret_cast<const uchar4*>(P.screen) + size_t(ja)*size_t(P.Ws);
-    const uchar4* rowb = reinterpret_cast<const uchar4*>(P.screen) + size_t(jb)*size_t(P.Ws);
-    const uchar4 c00 = __ldg(rowa + ia), c10 = __ldg(rowa + ib), c01 = __ldg(rowb + ia), c11 = __ldg(rowb + ib);
+    const unsigned int* rowa = reinterpret_cast<const unsigned int*>(P.screen) + size_t(ja)*size_t(P.Ws);
+    const unsigned int* rowb = reinterpret_cast<const unsigned int*>(P.screen) + size_t(jb)*size_t(P.Ws);
+    // bytes → floats with PRMT + one FADD per channel (widen3): integer → float conversions issue at a quarter rate
+    const vec3 c00 = widen3(__ldg(rowa + ia)), c10 = widen3(__ldg(rowa + ib));
+    const vec3 c01 = widen3(__ldg(rowb + ia)), c11 = widen3(__ldg(rowb + ib));
     const float w11 = a*b, w10 = a - w11, w01 = b - w11, w00 = (1.0f - a) - w01;
-    return mk3(w00*float(c00.x) + w10*float(c10.x) + w01*float(c01.x) + w11*float(c11.x),
-               w00*float(c00.y) + w10*float(c10.y) + w01*float(c01.y) + w11*float(c11.y),
-               w00*float(c00.z) + w10*float(c10.z) + w01*float(c01.z) + w11*float(c11.z));
+    return c00*w00 + c10*w10 + c01*w01 + c11*w11;
 }
 
 // Tile = 32 x 8 output pixels; rgb24 rows are staged in shared memory and leave as 32-bit words
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ Fina
     const bool inside = (x < P.W) && (y < P.H);
     unsigned int r8 = 0, g8 = 0, b8 = 0;
     if (inside) {
-        // astuv of the W×H final target (same rasteriser rule as make_frag)
-        const vec2 astuv = mk2(float((double(x) + 0.5)/double(P.W)), float((double(y) + 0.5)/double(P.H)));
+        // astuv of the W×H final target (same rasteriser rule as make_frag: float64 product, rounded once)
+        const vec2 astuv = mk2(float((double(x) + 0.5)*P.inv_W), float((double(y) + 0.5)*P.inv_H));
         vec3 rgb;
         if (P.subsample == 1) {
             rgb = screen_bilinear255(P, astuv)*(1.0f/255.0f);
@@ -191,10 +192,11 @@ __global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ Fina
             vec3 acc = mk3(0.0f);
             const vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
             const vec2 corner = astuv - (pixel_size/2.0f);
-            const vec2 origin = corner + (pixel_size/float(kernel))/2.0f;
+            const vec2 step = pixel_size/float(kernel);          // loop-invariant in the text too: same value
+            const vec2 origin = corner + step/2.0f;
             for (int sx = 0; sx < kernel; sx++)
                 for (int sy = 0; sy < kernel; sy++) {
-                    const vec2 offset = (pixel_size/float(kernel))*mk2(float(sx), float(sy));
+                    const vec2 offset = step*mk2(float(sx), float(sy));
                     acc = acc + screen_bilinear255(P, origin + offset);
                 }
             rgb = acc*((1.0f/255.0f)/float(kernel*kernel));
@@ -492,7 +494,7 @@ extern "C" int sfb_render_final(sfb_ctx* ctx, const void* screen_rgba8_dev, int 
     SFB_REQUIRE(subsample >= 1 && subsample <= 16, "sfb_render_final: subsample %d out of range", subsample);
     SFB_REQUIRE(components == 3 || components == 4, "sfb_render_final: components must be 3 or 4");
     FinalParams P{static_cast<const unsigned char*>(screen_rgba8_dev), screen_w, screen_h,
-                  width, height, subsample, components, static_cast<unsigned char*>(dst_dev)};
+                  width, height, subsample, components, static_cast<unsigned char*>(dst_dev), 1.0/double(width), 1.0/double(height)};
     dim3 block(32, 8), grid((width + 31)/32, (height + 7)/8);
     final_kernel<<<grid, block, 0, ctx->stream>>>(P);
     SFB_LAUNCH_CHECK(ctx);

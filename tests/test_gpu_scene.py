@@ -121,6 +121,47 @@ def test_export_sinks_and_frame_ranges(tmp_path):
     assert sorted(part) == [5, 6, 7, 8] and all(np.array_equal(part[k], plain[k]) for k in part)
 
 
+def test_frame_ranges_of_feedback_scenes_keep_their_history():
+    """MotionBlur averages the last 10 frames of its own output (temporal texture): exporting frames=(a, b) must
+    shade every frame before `a` too, or the range starts from an empty history and differs from the full export.
+    The same rule keeps such scenes from frame-sharding: under torchrun rank 0 exports them alone."""
+    import examples.demo as demo
+    demo.MotionBlur.background = demo.synthetic_background(160, 90)
+    try:
+        scene = demo.MotionBlur()
+        full = collect(scene, ssaa=1, subsample=1, time=24/60)
+        part = collect(scene, ssaa=1, subsample=1, time=24/60, frames=(14, 20))
+    finally:
+        demo.MotionBlur.background = None
+    assert sorted(part) == list(range(14, 20))
+    assert all(np.array_equal(part[k], full[k]) for k in part)
+    assert not np.array_equal(full[14], full[3])             # the history really changes the picture
+
+
+def test_a_failed_export_leaves_the_scene_usable(tmp_path):
+    """An exception in the frame loop (here: a user hook) must not leave the sink ring acquired or the render state
+    half-set: the next main() on the same scene works"""
+    import examples.demo as demo
+    scene = demo.ShaderToy()
+    def boom(index, pointer):
+        if index == 3:
+            raise KeyError("user hook failed")
+    with pytest.raises(KeyError):
+        scene.main(width=W, height=H, ssaa=1, subsample=1, time=0.2, on_frame=boom)
+    class Dies(demo.ShaderToy):
+        fail = True
+        def update(self):
+            if type(self).fail and self.frame_index == 4:
+                raise ValueError("module failed mid-export")
+    bad = Dies()
+    with pytest.raises(ValueError):
+        bad.main(width=W, height=H, ssaa=1, subsample=1, time=0.2, output=tmp_path/"bad.rgb")
+    assert bad.render_enabled and bad._frame_target is None
+    Dies.fail = False
+    path = bad.main(width=W, height=H, ssaa=1, subsample=1, time=0.2, output=tmp_path/"good.rgb")
+    assert np.fromfile(path, np.uint8).size == 12*H*W*3
+
+
 def test_unknown_glsl_is_an_error_and_hash_lookup_works():
     from examples.demo import ShaderScene
     from shaderflow_b200 import registry
