@@ -318,6 +318,12 @@ class ShaderTexture(ShaderModule):
 
     def handle(self, message):
         if self.track and isinstance(message, ShaderMessage.Shader.RecreateTextures):
+            # The reference recreates every tracked texture here (texture.py:250-270): what was RENDERED into it
+            # is gone, only data written with write() comes back. A single-box target is overwritten before it is
+            # read, so its GPU objects are kept; a texture with history (temporal / layers > 1) feeds earlier
+            # renders back into later ones and must start every export empty (zero-filled on creation).
+            if self.temporal > 1 or self.layers > 1:
+                self._made = None
             self.make()
 
     def pipeline(self) -> Iterable[ShaderVariable]:
