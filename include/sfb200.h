@@ -304,6 +304,26 @@ int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int back
                         int width, int height, int ssaa, int* rows_per_thread, int* window_rows);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Run-time compiled programs — the other half of ShaderProgram.compile (shader.py:313-349 hands ANY fragment text to
+ * the GL driver). A fragment this library has no ahead-of-time kernel for is translated GLSL → CUDA by the host side
+ * (shaderflow_b200/glsl) and compiled here:
+ *   sfb_jit_compile   NVRTC → a SASS image for sm_100a. `source` includes its headers by name from the in-memory table
+ *                     (header_names[i] → header_sources[i]). Needs no GPU; libnvrtc.so.12 is loaded on first use
+ *                     (SFB_ENOTFOUND when absent). *log (optional) receives the compiler's diagnostics, also on
+ *                     success; release image and log with sfb_jit_free. SFB_EINVAL = the source does not compile.
+ *   sfb_program_load  loads the image on ctx's device → *scene >= SFB_SCENE_PROGRAM_BASE, accepted by sfb_render_screen,
+ *                     sfb_render_target, sfb_render_frame and sfb_render_frame_probe like a built-in scene (the image
+ *                     must define the kernels sfb_jit_screen and sfb_jit_frame, csrc/jit/jit_kernels.cuh);
+ *                     n_samplers = samplers the program reads, in the order the caller will bind them. */
+#define SFB_SCENE_PROGRAM_BASE 1000
+enum { SFB_JIT_FMAD = 1 };   /* allow a*b+c → fma contraction (default: one rounding per operation, like the checker) */
+int sfb_jit_compile(const char* source, const char* const* header_names, const char* const* header_sources, int n_headers,
+                    int flags, void** image, size_t* image_bytes, char** log);
+void sfb_jit_free(void* image_or_log);
+int sfb_program_load(sfb_ctx* ctx, const void* image, size_t image_bytes, int n_samplers, int* scene);
+int sfb_program_unload(sfb_ctx* ctx, int scene);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Frame sink — replaces turbopipe.pipe/sync/done + fbo.read_into (exporting.py:140-174): a ring of
  * n_buffers device frames, each paired with a pinned host buffer; submit enqueues an async D2H on a copy
  * stream ordered after the render stream, a writer thread does write(fd) in submission order.

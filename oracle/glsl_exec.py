@@ -527,7 +527,12 @@ class Parser:
             if self.accept("["):
                 e = ("index", e, self.expr()); self.expect("]")
             elif self.accept("."):
-                e = ("field", e, self.next()[1])
+                name = self.next()[1]
+                if name == "length" and self.peek()[1] == "(":
+                    self.next(); self.expect(")")
+                    e = ("length", e)
+                else:
+                    e = ("field", e, name)
             elif self.peek()[1] in ("++", "--") and self.peek()[0] == "op":
                 e = ("postinc", self.next()[1], e)
             else:
@@ -962,6 +967,10 @@ class Machine:
             return self.field(self.eval(node[1], mask), node[2])
         if kind == "index":
             return self.index(self.eval(node[1], mask), self.eval(node[2], mask))
+        if kind == "length":                       # .length() of an array, a vector (components) or a matrix (columns)
+            v = self.eval(node[1], mask)
+            n = len(v.a) if isinstance(v.a, list) else v.a.shape[1]
+            return V("int", np.asarray([n], I32))
         if kind == "construct":
             return self.construct(node[1], [self.eval(a, mask) for a in node[2]])
         if kind == "call":

@@ -24,6 +24,8 @@ FILTER_EXACT, FILTER_HARDWARE, RENDER_LITERAL, RENDER_TILED = 0, 1, 2, 4
 PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32, PCM_F64 = range(6)
 SCALARS = 5
 SCENE_COUNT = 17
+SCENE_PROGRAM_BASE = 1000
+JIT_FMAD = 1
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
 
 
@@ -132,6 +134,11 @@ _PROTOTYPES = dict(
     sfb_sink_finish=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     sfb_sink_abort=(c_int, [c_void_p]),
     sfb_sink_close=(c_int, [c_void_p]),
+    sfb_jit_compile=(c_int, [c_char_p, POINTER(c_char_p), POINTER(c_char_p), c_int, c_int, POINTER(c_void_p), POINTER(c_size_t),
+                             POINTER(c_void_p)]),
+    sfb_jit_free=(None, [c_void_p]),
+    sfb_program_load=(c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_int)]),
+    sfb_program_unload=(c_int, [c_void_p, c_int]),
 )
 
 _lib = None
@@ -161,6 +168,32 @@ def check(code: int) -> None:
     if code != OK:
         message = lib().sfb_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libsfb200: {message} (code {code})")
+
+
+class CompileError(RuntimeError):
+    """sfb_jit_compile rejected the source; `.log` holds the compiler's diagnostics"""
+    def __init__(self, message: str, log: str):
+        super().__init__(message + ("\n" + log if log else ""))
+        self.log = log
+
+
+def jit_compile(source: str, headers: dict[str, str], flags: int = 0) -> tuple[bytes, str]:
+    """CUDA source + in-memory headers → (SASS image for sm_100a, compile log). Needs NVRTC, not a GPU."""
+    names = (c_char_p*len(headers))(*[k.encode() for k in headers])
+    texts = (c_char_p*len(headers))(*[v.encode() for v in headers.values()])
+    image, size, log = c_void_p(), c_size_t(), c_void_p()
+    code = lib().sfb_jit_compile(source.encode(), names, texts, len(headers), flags, byref(image), byref(size), byref(log))
+    text = C.string_at(log).decode("utf-8", "replace") if log else ""
+    if log:
+        lib().sfb_jit_free(log)
+    if code != OK:
+        message = lib().sfb_last_error().decode("utf-8", "replace")
+        if code == EINVAL:
+            raise CompileError(f"libsfb200: {message}", text)
+        raise RuntimeError(f"libsfb200: {message} (code {code})")
+    data = C.string_at(image, size.value)
+    lib().sfb_jit_free(image)
+    return data, text
 
 
 def _ptr(obj) -> c_void_p | None:
@@ -446,6 +479,15 @@ class Context:
     def pcm_ingest(self, raw, n_frames: int, channels: int, fmt: int, planar, clip_samples: int, offset: int) -> None:
         """Interleaved file samples (device bytes) → rows [offset, offset+n_frames) of the planar float32 clip"""
         check(lib().sfb_pcm_ingest(self.handle, _ptr(raw), n_frames, channels, fmt, _ptr(planar), clip_samples, offset))
+
+    def program_load(self, image: bytes, n_samplers: int) -> int:
+        """SASS image of a run-time compiled program → scene id (>= SCENE_PROGRAM_BASE) for the render_* calls"""
+        scene = c_int()
+        check(lib().sfb_program_load(self.handle, image, len(image), n_samplers, byref(scene)))
+        return scene.value
+
+    def program_unload(self, scene: int) -> None:
+        check(lib().sfb_program_unload(self.handle, scene))
 
     def destroy(self) -> None:
         if self.handle:

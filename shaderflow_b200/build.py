@@ -19,7 +19,7 @@ PACKAGE = Path(__file__).resolve().parent
 CSRC = PACKAGE/"csrc"
 OBJ = CSRC/"build"
 LIBRARY = PACKAGE/"libsfb200.so"
-UNITS = ("core.cu", "audio.cu", "render.cu", "render_screen.cu", "render_frame.cu", "render_lanes.cu", "visualizer_tiled_1.cu", "visualizer_tiled_2.cu", "visualizer_tiled_3.cu", "visualizer_tiled_4.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu", "ingest.cu")
+UNITS = ("core.cu", "audio.cu", "render.cu", "render_screen.cu", "render_frame.cu", "render_lanes.cu", "visualizer_tiled_1.cu", "visualizer_tiled_2.cu", "visualizer_tiled_3.cu", "visualizer_tiled_4.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu", "ingest.cu", "jit.cu")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objects = [OBJ/(Path(u).stem + ".o") for u in UNITS]
     if force or jobs or stale(LIBRARY, objects):
         link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-                "-o", str(LIBRARY), *map(str, objects), "-lpthread", "-lrt"]
+                "-o", str(LIBRARY), *map(str, objects), "-lpthread", "-lrt", "-ldl"]
         done = subprocess.run(link, capture_output=True, text=True)
         if done.returncode:
             sys.stderr.write(done.stdout + done.stderr)

@@ -233,8 +233,23 @@ extern "C" int sfb_scene_info_get(int scene, sfb_scene_info* info) {
 
 static int fill_params(RenderParams& P, const char* who, int scene, const sfb_uniforms* uniforms,
                        sfb_tex* const* samplers, int n_samplers, int flags) {
-    SFB_REQUIRE(scene >= 0 && scene < SFB_SCENE_COUNT, "%s: bad scene %d", who, scene);
     SFB_REQUIRE(uniforms, "%s: null uniforms", who);
+    if (scene >= SFB_SCENE_PROGRAM_BASE) {                        // a run-time compiled program (jit.cu)
+        int device = 0;
+        SFB_CUDA(cudaGetDevice(&device));
+        const int needed = sfb_program_samplers(scene, device);
+        SFB_REQUIRE(needed >= 0, "%s: %d is not a loaded program of device %d", who, scene, device);
+        SFB_REQUIRE(n_samplers >= needed && n_samplers <= SFB_MAX_SAMPLERS, "%s: the program reads %d samplers, got %d", who, needed, n_samplers);
+        P.u = *uniforms;
+        for (int i = 0; i < n_samplers; i++) {
+            SFB_REQUIRE(samplers && samplers[i], "%s: sampler %d is null", who, i);
+            P.tex[i] = samplers[i]->dev();
+            SFB_REQUIRE(P.tex[i].lin, "%s: sampler %d has no storage", who, i);
+        }
+        P.fast = 0;
+        return SFB_OK;
+    }
+    SFB_REQUIRE(scene >= 0 && scene < SFB_SCENE_COUNT, "%s: bad scene %d", who, scene);
     SFB_REQUIRE(n_samplers >= SCENES[scene].n_required && n_samplers <= SFB_MAX_SAMPLERS,
         "%s: scene '%s' needs %d samplers, got %d", who, SCENES[scene].name, SCENES[scene].n_required, n_samplers);
     if (scene == SFB_SCENE_MOTIONBLUR)
@@ -338,7 +353,8 @@ extern "C" int sfb_render_screen(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     P.dst_dtype = SFB_DTYPE_U8; P.dst_padded = 4;
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && !dst_f32_dev)
         return visualizer_screen_pass(ctx, P, samplers[0], flags);
-    if (int e = sfb_launch_screen(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream)) return e;
+    if (int e = (scene >= SFB_SCENE_PROGRAM_BASE) ? sfb_program_launch(scene, 0, P, ctx->stream)
+                                                  : sfb_launch_screen(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream)) return e;
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
 }
@@ -359,7 +375,8 @@ extern "C" int sfb_render_target(sfb_ctx* ctx, int scene, const sfb_uniforms* un
     target->array_stale = true;                   // the cudaArray copy is old: sample through the linear mirror
     if (scene == SFB_SCENE_VISUALIZER && P.fast && !(flags & SFB_FILTER_HARDWARE) && target->dtype == SFB_DTYPE_U8 && target->padded == 4)
         return visualizer_screen_pass(ctx, P, samplers[0], flags);
-    if (int e = sfb_launch_screen(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream)) return e;
+    if (int e = (scene >= SFB_SCENE_PROGRAM_BASE) ? sfb_program_launch(scene, 0, P, ctx->stream)
+                                                  : sfb_launch_screen(scene, (flags & SFB_FILTER_HARDWARE) != 0, P, ctx->stream)) return e;
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
 }
@@ -423,6 +440,11 @@ static int render_frame(sfb_ctx* ctx, int scene, const sfb_uniforms* uniforms,
         return SFB_OK;
     }
     const bool hw = (flags & SFB_FILTER_HARDWARE) != 0;
+    if (scene >= SFB_SCENE_PROGRAM_BASE) {
+        if (int e = sfb_program_launch(scene, 1, P, ctx->stream)) return e;
+        SFB_LAUNCH_CHECK(ctx);
+        return SFB_OK;
+    }
     // the ALU-bound scenes at ssaa 2 / 4: one lane per sub-sample (render_lanes.cu); everything else one thread per pixel
     if ((flags & SFB_RENDER_LITERAL) || !sfb_launch_frame_lanes(scene, hw, P, ctx->stream))
         if (int e = sfb_launch_frame(scene, hw, P, ctx->stream)) return e;

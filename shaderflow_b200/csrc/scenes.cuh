@@ -8,18 +8,7 @@
 
 namespace glsl {
 
-struct RenderParams {
-    sfb_uniforms u;
-    DevSampler tex[SFB_MAX_SAMPLERS];
-    int Wr, Hr;              // fragments of the iScreen target (render resolution)
-    int W, H;                // final resolution
-    int ssaa, subsample, comps;
-    double inv_Wr, inv_Hr;   // 1/Wr, 1/Hr
-    unsigned char* dst;
-    int dst_dtype, dst_padded;   // format of `dst` for sfb_render_target (SFB_DTYPE_*, stored components)
-    float* dst_f32;
-    int fast;                // scene-specific fast path allowed (set by the launcher after checking formats)
-};
+using ::RenderParams;
 
 struct Frag { vec2 agluv, gluv, astuv, stuv, stxy, glxy; };
 

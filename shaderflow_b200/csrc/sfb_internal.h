@@ -38,17 +38,7 @@ struct sfb_ctx {
 
 int sfb_ctx_scratch(sfb_ctx* ctx, size_t bytes, void** out);
 
-// What a kernel sees of a texture (passed by value inside the kernel parameter block)
-struct DevSampler {
-    unsigned long long hw;   // cudaTextureObject_t, 0 when only the linear mirror is valid
-    const void* lin;         // [h][w][padded] texels, tightly packed
-    int w, h;
-    int padded;              // components as stored: 1, 2 or 4
-    int comps;               // components the user declared (3 → alpha reads 1)
-    int dtype;               // SFB_DTYPE_*
-    int filter;              // SFB_FILTER_NEAREST / LINEAR
-    int rx, ry;              // repeat (1) or clamp-to-edge (0)
-};
+#include "render_params.h"
 
 struct sfb_tex {
     sfb_ctx* ctx = nullptr;
@@ -71,3 +61,7 @@ struct sfb_tex {
         return s;
     }
 };
+
+// Run-time compiled programs (jit.cu): scene ids >= SFB_SCENE_PROGRAM_BASE
+int sfb_program_samplers(int scene, int device);          // samplers the program reads; -1 = not a program of this device
+int sfb_program_launch(int scene, int kind, const RenderParams& P, cudaStream_t stream);   // kind 0 screen, 1 fused frame

@@ -152,14 +152,42 @@ class ShaderProgram(ShaderModule):
             return self
         name = registry.resolve(self._fragment)
         if name is None:
-            names = [N.scene_info(i)["name"] for i in range(N.SCENE_COUNT)]
-            raise RuntimeError(logger.error(
-                f"ShaderProgram '{self.name}': this fragment shader is not one the CUDA backend has a "
-                f"kernel for (digest {registry.digest(self.fragment)}). Built-in scenes: {names}. "
-                "Add `// sfb200: scene=<name>` to select one explicitly."))
+            return self._compile_runtime()
         self.scene_id = N.scene_lookup(name)
         self.scene_info = N.scene_info(self.scene_id)
         return self
+
+    def _compile_runtime(self) -> "ShaderProgram":
+        """A fragment no ahead-of-time kernel exists for: translate the GLSL to CUDA and compile it now, as the
+        reference hands any text to the GL driver (shader.py:313-349). The header in front of the user's text is
+        what `_build_shader` assembles (shader.py:190-239): every pipeline variable's declaration and the modules'
+        defines (texture aliases and accessors); the std-lib (shaderflow.glsl, camera.glsl) comes from
+        csrc/jit/shaderflow_rt.cuh. Raises RuntimeError with the translator's / compiler's diagnostics."""
+        from shaderflow_b200 import glsl
+        header, seen = [], set()
+        for variable in self.full_pipeline():
+            if variable.name not in seen:
+                seen.add(variable.name)
+                header.append(variable.declaration)
+        for module in self.scene.modules:
+            header.extend(module.defines() or ())
+        try:
+            image, translation, _ = glsl.build(self.fragment, "\n".join(header))
+        except (glsl.TranslationError, N.CompileError) as error:
+            raise RuntimeError(logger.error(
+                f"ShaderProgram '{self.name}': the fragment shader could not be compiled for the CUDA backend: {error}")) from None
+        self.release_runtime()
+        self.scene_id = self._runtime_scene = self.scene.cuda.program_load(image, len(translation.samplers))
+        self.scene_info = dict(name=f"runtime:{registry.digest(self.fragment)}", extra=list(translation.extra),
+                               samplers=list(translation.samplers), required=len(translation.samplers))
+        return self
+
+    _runtime_scene: Optional[int] = None
+
+    def release_runtime(self) -> None:
+        if self._runtime_scene is not None and self.scene.cuda is not None:
+            self.scene.cuda.program_unload(self._runtime_scene)
+        self._runtime_scene = None
 
     # -- uniforms ------------------------------------------------------------------------------
     _plan: Any = None

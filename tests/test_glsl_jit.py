@@ -1,0 +1,132 @@
+"""Run-time GLSL → CUDA path, the part that needs no GPU: the translator (shaderflow_b200/glsl) and NVRTC through the
+C ABI (sfb_jit_compile). The compiled programs run in tests/test_gpu_jit.py."""
+import ctypes.util
+from pathlib import Path
+
+import pytest
+
+from shaderflow_b200 import _native as N
+from shaderflow_b200 import glsl
+from shaderflow_b200.glsl import cuda as emit
+from tests import jit_cases as J
+
+REFERENCE = Path("/root/reference")
+needs_nvrtc = pytest.mark.skipif(not (ctypes.util.find_library("nvrtc") or Path("/usr/local/cuda/lib64/libnvrtc.so.12").exists()),
+                                 reason="libnvrtc is not installed")
+
+
+def body(source: str) -> str:
+    return source[source.index("// functions"):]
+
+
+def test_swizzles_literals_and_out_parameters():
+    t = glsl.translate("""
+        float f(inout vec3 v, out float w, vec2 p) { v.zx = p.yx*0.1; v.y += 1; w = v.xyz.z; return v[1]; }
+        void main() { vec3 a = vec3(1); float w; fragColor = vec4(a.bgr, f(a, w, gluv)); fragColor.a = 1e-3; }""")
+    code = body(t.source)
+    assert "G_DEV float f(vec3& v, float& w, vec2 p)" in code
+    assert "swz_set<2, 0>(v, (swz<1, 0>(p) * 0.100000001f))" in code           # the float32 value of 0.1
+    assert "(v.y += 1)" in code and "swz<0, 1, 2>(v).z" in code and "v[1]" in code
+    assert "swz<2, 1, 0>(a)" in code and "(fragColor.a = 0.00100000005f)" in code
+    assert t.extra == [] and t.samplers == []
+
+
+def test_struct_fields_win_over_swizzle_names_and_structs_get_constructors():
+    t = glsl.translate("struct Pair { vec2 xy; float st; }; void main() { Pair p = Pair(gluv, 1); fragColor = vec4(p.xy, p.st, p.xy.yx.x); }")
+    assert "G_DEV Pair(vec2 xy_, float st_) : xy(xy_), st(st_) {}" in t.source
+    assert "vec4(p.xy, p.st, swz<1, 0>(p.xy).x)" in t.source
+
+
+def test_only_what_main_reaches_takes_a_slot():
+    header = "\n".join(f"uniform float iUnused{i};" for i in range(40)) + """
+        uniform sampler2D a0x0; uniform sampler2D b0x0; uniform vec3 iTint; uniform int iMode; uniform float iTime;
+        #define a a0x0
+        vec4 bTexture(int t, int l, vec2 uv) { return texture(b0x0, uv); }
+        float helper(float x) { return x*iUnused3; }"""
+    t = glsl.translate("void main() { fragColor = texture(a, astuv)*vec4(iTint, iTime) + float(iMode); }", header)
+    assert t.extra == ["iTint", "iMode"] and t.extra_types == ["vec3", "int"] and t.samplers == ["a0x0"]
+    assert "iTime" not in t.extra                                               # a fixed field of sfb_uniforms
+    assert "bTexture" not in t.source and "helper" not in t.source and "iUnused" not in t.source
+    assert "vec3 iTint = sfb_extra<vec3>(0);" in t.source and "sampler2D a0x0 = sfb_sampler(0);" in t.source
+
+
+def test_arrays_constants_loops_and_discard():
+    t = glsl.translate("""
+        const float K[3] = float[](1., 2., 3.);
+        float pick(int i) { if (i > 2) discard; return K[i]; }
+        void main() { float s = 0; for (int i = 0; i < K.length(); ++i) { s += pick(i); } fragColor = vec4(s); }""")
+    assert "const float K[3] = {float(1.0f), float(2.0f), float(3.0f)};" in t.source
+    assert "{ sfb_discarded = true; return float(); }" in t.source
+    assert "for (; (i < length_of(K)); (++i))" in t.source
+
+
+def test_translation_errors_are_reported():
+    with pytest.raises(glsl.TranslationError, match="no main"):
+        glsl.translate("float f() { return 1.0; }")
+    with pytest.raises(glsl.TranslationError, match="dFdx"):
+        glsl.translate("void main() { fragColor = vec4(dFdx(gluv.x)); }")
+    with pytest.raises(glsl.TranslationError, match="expected"):
+        glsl.translate("void main() { fragColor = vec4(1.0) }")
+    many = "".join(f"uniform float u{i};" for i in range(17))
+    with pytest.raises(glsl.TranslationError, match="more than 16"):
+        glsl.translate("void main() { fragColor = vec4(" + "+".join(f"u{i}" for i in range(17)) + "); }", many)
+    with pytest.raises(glsl.TranslationError, match="mat3"):
+        glsl.translate("uniform mat3 m; void main() { fragColor = vec4(m[0], 1); }")
+
+
+def test_float_literals_carry_the_float32_value():
+    assert emit.float_literal(0.1) == "0.100000001f" and emit.float_literal(1.0) == "1.0f" and emit.float_literal(1e-3) == "0.00100000005f"
+    assert emit.float_literal(1e39) == "__int_as_float(0x7f800000)" and emit.float_literal(16777217.0) == "16777216.0f"
+
+
+@needs_nvrtc
+@pytest.mark.parametrize("name", J.CORPUS + ("stdlib",))
+def test_corpus_compiles_to_sass(name):
+    header = J.STDLIB_HEADER if name == "stdlib" else J.HEADER
+    image, translation, log = glsl.build((J.SHADERS/f"{name}.frag").read_text(), header)
+    assert image[:4] == b"\x7fELF" and len(image) > 10_000
+    assert b"sfb_jit_screen" in image and b"sfb_jit_frame" in image
+    assert "error" not in log.lower()
+    if name == "textured":
+        assert translation.samplers == ["picture", "table"] and translation.extra == ["iGain"]
+
+
+@needs_nvrtc
+def test_compile_errors_carry_the_compiler_log():
+    with pytest.raises(N.CompileError) as info:
+        glsl.build("void main() { fragColor = undeclared_function(gluv); }")
+    assert "undeclared_function" in str(info.value) and info.value.log
+
+
+REFERENCE_SCENES = ["Basic", "ShaderToy", "Visualizer", "MusicBars", "Waveform", "Mandelbrot", "Tetration", "RayMarch",
+                    "MultiShader", "Multipass", "Dynamics", "Audio", "Life"]
+_REFERENCE_SCRIPT = """
+import json, sys
+sys.path.insert(0, sys.argv[1])
+from oracle import ref_scene
+from shaderflow_b200 import _native as N, glsl
+done = {}
+for scene in sys.argv[2:]:
+    for name, program in ref_scene.capture(scene)["programs"].items():
+        translation = glsl.translate(program["fragment"])
+        image, _ = N.jit_compile(glsl.program(translation), glsl.headers())
+        done[scene + "." + name] = [image[:4] == b"\\x7fELF", translation.extra, translation.samplers]
+print("RESULT " + json.dumps(done))
+"""
+
+
+@needs_nvrtc
+@pytest.mark.reference
+@pytest.mark.skipif(not REFERENCE.exists(), reason="needs /root/reference (build container)")
+def test_the_references_own_assembled_programs_translate_and_compile():
+    """The text the reference hands to the GL driver — its header, its whole std-lib and camera include, the example's
+    fragment — goes through the translator and NVRTC unchanged (the reference's GLSL definitions then replace the CUDA
+    std-lib entries of the same name). In a child process: importing the reference rebinds the `shaderflow` name."""
+    import json, subprocess, sys
+    root = str(Path(__file__).resolve().parents[1])
+    run = subprocess.run([sys.executable, "-c", _REFERENCE_SCRIPT, root, *REFERENCE_SCENES], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stderr[-3000:]
+    done = json.loads(next(line for line in run.stdout.splitlines() if line.startswith("RESULT "))[7:])
+    assert len(done) == 2*len(REFERENCE_SCENES) + 2 and all(ok for ok, _, _ in done.values()), done     # + MultiShader.child, Life.iLife
+    assert done["Visualizer.iScreen"][1:] == [["iAudioVolume", "iAudioSTD"], ["iWaveform0x0", "iSpectrogram0x0", "background0x0"]]
+    assert done["Life.iLife"][1:] == [["iLifePeriod", "iLifeSize"], ["iLife1x0"]]

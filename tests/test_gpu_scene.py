@@ -162,15 +162,25 @@ def test_a_failed_export_leaves_the_scene_usable(tmp_path):
     assert np.fromfile(path, np.uint8).size == 12*H*W*3
 
 
-def test_unknown_glsl_is_an_error_and_hash_lookup_works():
+def test_unknown_glsl_is_compiled_at_run_time_and_hash_lookup_works():
+    """A fragment the registry does not recognise goes through the GLSL → CUDA translator (tests/test_gpu_jit.py holds
+    that path to the evaluator); text that is not GLSL is an error naming what the compiler did not accept"""
     from examples.demo import ShaderScene
     from shaderflow_b200 import registry
     class Custom(ShaderScene):
         def build(self):
             self.shader.fragment = "void main() { fragColor = vec4(1.0); }"
     scene = Custom()
-    with pytest.raises(RuntimeError, match="not one the CUDA backend has a kernel for"):
-        scene.main(width=64, height=36, time=0.1)
+    seen = []
+    def grab(index, pointer):
+        scene.cuda.sync(); seen.append(scene.frame_tensor.cpu().numpy().copy())
+    scene.main(width=64, height=36, time=0.1, on_frame=grab)
+    assert scene.shader.scene_id >= 1000 and len(seen) == 6 and all((f == 255).all() for f in seen)
+    class Broken(ShaderScene):
+        def build(self):
+            self.shader.fragment = "void main() { fragColor = vec4(1.0) }"
+    with pytest.raises(RuntimeError, match="could not be compiled for the CUDA backend"):
+        Broken().main(width=64, height=36, time=0.1)
     assert {"default", "shadertoy", "visualizer", "bars", "waveform", "mandelbrot", "tetration", "raymarch",
             "multipass", "motionblur", "life_simulation", "life_visuals"} <= set(registry.KNOWN_HASHES.values())
 
