@@ -86,6 +86,26 @@ def swizzle_indices(name: str) -> str:
     return ", ".join(str(s.index(c)) for c in name)
 
 
+def is_constant(e, known: set) -> bool:
+    """A scalar constant expression C++ can evaluate at compile time (array bounds, case labels need one)"""
+    if e is None:
+        return False
+    kind = e[0]
+    if kind == "lit":
+        return True
+    if kind == "name":
+        return e[1] in known
+    if kind == "unary":
+        return is_constant(e[2], known)
+    if kind == "binary":
+        return is_constant(e[2], known) and is_constant(e[3], known)
+    if kind == "ternary":
+        return all(is_constant(x, known) for x in e[1:4])
+    if kind == "construct":
+        return e[1] in F.SCALARS and len(e[2]) == 1 and is_constant(e[2][0], known)
+    return False
+
+
 def names_used(node, out: set) -> None:
     if isinstance(node, tuple):
         if node and node[0] == "name":
@@ -309,6 +329,7 @@ class Emitter:
 
         self.put("// uniforms, globals")
         declared: set = set()
+        constants: set = set()
         for item in self.items:
             if item[0] != "global":
                 continue
@@ -349,7 +370,11 @@ class Emitter:
                         continue
                     declared.add(name)
                     d, i = self.declarator(t, name, init)
-                    self.put(("const " if "const" in quals else "") + d + i + ";")
+                    if "const" in quals and t in F.SCALARS and is_constant(init, constants):
+                        constants.add(name)                    # usable as an array bound or a case label
+                        self.put(f"static constexpr {d}{i};")
+                    else:
+                        self.put(("const " if "const" in quals else "") + d + i + ";")
 
         self.put("// functions")
         for item in self.items:
