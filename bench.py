@@ -258,7 +258,7 @@ def other_configs(local: int, hbm_peak: float, cpu: bool) -> dict:
     entry = dict(frames_per_s=frames/(ms/1e3), ms_per_frame=ms/frames, frames=frames,
                  e2e=dict(value=frames/(ms_e2e/1e3), unit="frames/s", d2h_bytes_per_frame=1920*1080*3),
                  gfragments_per_s=1920*1080*frames/(ms/1e3)/1e9,
-                 kernels="visualizer_rows_kernel<1, 3, 96> (RGBA8 iScreen) + final_kernel (final.glsl, subsample 2): not a box "
+                 kernels="visualizer_rows_kernel<1, 3, 96> (RGBA8 iScreen) + final_half_step_kernel (final.glsl, subsample 2): not a box "
                          "filter at ssaa 1, so the two passes stay separate",
                  roofline=dict(bound="hbm", achieved=algorithmic*frames/(ms/1e3)/1e9, peak=hbm_peak, unit="GB/s",
                                frac=algorithmic*frames/(ms/1e3)/1e9/hbm_peak, algorithmic_bytes_per_frame=algorithmic,
