@@ -1067,6 +1067,13 @@ class Machine:
                 arr[:, k] = val.a
                 self.assign(target[1], V(base.t, arr), mask)
                 return val
+            if isinstance(base.t, str) and base.t.startswith("mat"):          # m[k] = column
+                val = self.convert(val, "vec" + base.t[3])
+                lanes = max(base.a.shape[0], val.a.shape[0])
+                arr = np.broadcast_to(base.a, (lanes,) + base.a.shape[1:]).copy()
+                arr[:, k, :] = val.a
+                self.assign(target[1], V(base.t, arr), mask)
+                return val
         raise GLSLError(f"not an lvalue: {kind}")
 
     # ---- operators
@@ -1264,6 +1271,8 @@ class Machine:
             if all(p[1] == a.t for p, a in zip(f[3], args)):
                 return f
         def convertible(a, t):
+            if not isinstance(a.t, str) or not isinstance(t, str):          # arrays: same element type
+                return (not isinstance(a.t, str)) and (not isinstance(t, str)) and a.t[1] == t[1]
             ia, ib = vec_info(a.t), (vec_info(t) if isinstance(t, str) else None)
             return a.t == t or (ia and ib and ia[1] == ib[1] and ia[0] in ("int", "uint") and ib[0] == "float") \
                 or (ia and ib and ia[1] == ib[1] and ia[0] == "int" and ib[0] == "uint")
@@ -1454,6 +1463,23 @@ class Machine:
     def b_notEqual(self, x, y): return self._compare(np.not_equal, x, y)
 
     def b_transpose(self, m): return V(m.t, np.swapaxes(m.a, 1, 2).copy())
+
+    def b_determinant(self, m):
+        a = m.a.astype(F32)
+        if m.t == "mat2":
+            return V("float", (a[:, 0, 0]*a[:, 1, 1] - a[:, 1, 0]*a[:, 0, 1]).astype(F32))
+        return V("float", np.linalg.det(np.swapaxes(a, 1, 2).astype(np.float64)).astype(F32))
+
+    def b_inverse(self, m):
+        a = m.a.astype(F32)
+        if m.t == "mat2":                                  # adjugate / determinant, one float32 rounding per operation
+            d = (F32(1)/self.b_determinant(m).a).astype(F32)
+            out = np.empty_like(a)
+            out[:, 0, 0], out[:, 0, 1] = a[:, 1, 1]*d, -a[:, 0, 1]*d
+            out[:, 1, 0], out[:, 1, 1] = -a[:, 1, 0]*d, a[:, 0, 0]*d
+            return V(m.t, out.astype(F32))
+        inv = np.linalg.inv(np.swapaxes(a, 1, 2).astype(np.float64))
+        return V(m.t, np.swapaxes(inv, 1, 2).astype(F32))
 
     # texture access: OpenGL fixed function, restated in oracle/glsl_np.Texture
     def b_texture(self, sampler, uv, bias=None):

@@ -341,15 +341,22 @@ G_DEV float half_bits_to_float(unsigned short h) { float f; asm("cvt.f32.f16 %0,
 G_DEV vec4 texel_at(const DevSampler& s, int ix, int iy) {
     ix = wrap_index(ix, s.w, s.rx);
     iy = wrap_index(iy, s.h, s.ry);
-    const size_t idx = (size_t(iy)*size_t(s.w) + size_t(ix))*size_t(s.padded);
-    float c[4] = {0.0f, 0.0f, 0.0f, 1.0f};
-    for (int k = 0; k < s.padded; k++) {
-        if (s.dtype == SFB_DTYPE_U8)       c[k] = float(__ldg(static_cast<const unsigned char*>(s.lin) + idx + k))/255.0f;
-        else if (s.dtype == SFB_DTYPE_F32) c[k] = __ldg(static_cast<const float*>(s.lin) + idx + k);
-        else                               c[k] = half_bits_to_float(__ldg(static_cast<const unsigned short*>(s.lin) + idx + k));
+    const size_t idx = size_t(iy)*size_t(s.w) + size_t(ix);
+    vec4 t(0.0f, 0.0f, 0.0f, 1.0f);
+    if (s.dtype == SFB_DTYPE_U8) {
+        if (s.padded == 4) { const uchar4 c = __ldg(static_cast<const uchar4*>(s.lin) + idx); t = vec4(c.x/255.0f, c.y/255.0f, c.z/255.0f, c.w/255.0f); }
+        else if (s.padded == 2) { const uchar2 c = __ldg(static_cast<const uchar2*>(s.lin) + idx); t.x = c.x/255.0f; t.y = c.y/255.0f; }
+        else t.x = __ldg(static_cast<const unsigned char*>(s.lin) + idx)/255.0f;
+    } else if (s.dtype == SFB_DTYPE_F32) {
+        if (s.padded == 4) { const float4 c = __ldg(static_cast<const float4*>(s.lin) + idx); t = vec4(c.x, c.y, c.z, c.w); }
+        else if (s.padded == 2) { const float2 c = __ldg(static_cast<const float2*>(s.lin) + idx); t.x = c.x; t.y = c.y; }
+        else t.x = __ldg(static_cast<const float*>(s.lin) + idx);
+    } else {
+        const unsigned short* p = static_cast<const unsigned short*>(s.lin) + idx*size_t(s.padded);
+        for (int k = 0; k < s.padded; k++) t.v[k] = half_bits_to_float(__ldg(p + k));
     }
-    if (s.comps == 3) c[3] = 1.0f;
-    return vec4(c[0], c[1], c[2], c[3]);
+    if (s.comps == 3) t.w = 1.0f;
+    return t;
 }
 G_DEV vec4 texture(sampler2D t, vec2 uv) {
     const DevSampler& s = *t.s;

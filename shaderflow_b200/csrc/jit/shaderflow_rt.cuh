@@ -212,10 +212,17 @@ struct ShaderBase {
         sfb_discarded = false;
     }
     G_DEV sampler2D sfb_sampler(int slot) const { sampler2D s; s.s = &sfb_params->tex[slot]; return s; }
+    // module / user uniforms: float components as floats, int / uint / bool components as their 32 bits
     template <class T> G_DEV T sfb_extra(int slot) const {
         const float* e = sfb_params->u.extra[slot];
-        if constexpr (info<T>::n == 1) return T(e[0]);
-        else return T(vec4(e[0], e[1], e[2], e[3]));
+        using B = typename info<T>::base;
+        if constexpr (B(0.5) != B(0)) {                          // float
+            if constexpr (info<T>::n == 1) return T(e[0]);
+            else return T(vec4(e[0], e[1], e[2], e[3]));
+        } else {
+            if constexpr (info<T>::n == 1) return T(__float_as_int(e[0]));
+            else return T(ivec4(__float_as_int(e[0]), __float_as_int(e[1]), __float_as_int(e[2]), __float_as_int(e[3])));
+        }
     }
 
     G_DEV vec2 agluv2gluv(vec2 p) const { return p*vec2(iAspectRatio, 1); }                                        // :99-100

@@ -8,6 +8,8 @@ from __future__ import annotations
 from pathlib import Path
 from typing import Any, Iterable, Optional, Union
 
+import ctypes as C
+
 import numpy as np
 from attrs import Factory, define
 
@@ -48,9 +50,10 @@ def _scalars(value) -> list:
     return np.asarray(value, dtype=np.float64).ravel().tolist()
 
 
-def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[str]) -> N.Uniforms:
+def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[str], extra_types: Optional[list[str]] = None) -> N.Uniforms:
     """name → value table of a pipeline → the POD block; numpy scalars/vectors cast to float32 like
-    GL uniform uploads do (ctypes stores the float32 rounding of the Python float)"""
+    GL uniform uploads do (ctypes stores the float32 rounding of the Python float). `extra_types` (run-time compiled
+    programs): GLSL type per slot — int / uint / bool components travel as their 32 bits, not as float values"""
     kinds = _FIELD_KINDS
     for name, value in values.items():
         kind = kinds.get(name)
@@ -71,6 +74,10 @@ def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[s
             raise RuntimeError(f"Uniform '{name}' required by the shader is not in the scene's pipeline")
         flat = _scalars(value)
         row = block.extra[slot]
+        if extra_types is not None and not extra_types[slot].startswith(("float", "vec")):
+            bits = np.asarray([int(v) & 0xFFFFFFFF for v in flat[:4]], dtype=np.uint32).view(np.float32)
+            C.memmove(row, bits.ctypes.data, bits.nbytes)         # bit patterns: no float conversion (NaN payloads survive)
+            continue
         for i in range(min(4, len(flat))):
             row[i] = flat[i]
     return block
@@ -163,7 +170,21 @@ class ShaderProgram(ShaderModule):
         what `_build_shader` assembles (shader.py:190-239): every pipeline variable's declaration and the modules'
         defines (texture aliases and accessors); the std-lib (shaderflow.glsl, camera.glsl) comes from
         csrc/jit/shaderflow_rt.cuh. Raises RuntimeError with the translator's / compiler's diagnostics."""
+        import os
         from shaderflow_b200 import glsl
+        fragment = self.fragment
+        # `#include "file"` lines resolve against the fragment's own directory and include_directories (shader.py:186,231-235)
+        roots = [Path(self._fragment).parent] if isinstance(self._fragment, Path) else []
+        roots += [Path(d) for d in self.include_directories]
+        def include(match, depth=[0]):
+            for root in roots:
+                if (root/match.group(1)).is_file():
+                    depth[0] += 1
+                    if depth[0] > 64:
+                        raise RuntimeError(f"ShaderProgram '{self.name}': #include nesting too deep ({match.group(1)})")
+                    return self._include_regex.sub(include, (root/match.group(1)).read_text())
+            raise RuntimeError(f"ShaderProgram '{self.name}': #include \"{match.group(1)}\" not found in {[str(r) for r in roots]}")
+        fragment = self._include_regex.sub(include, fragment)
         header, seen = [], set()
         for variable in self.full_pipeline():
             if variable.name not in seen:
@@ -172,17 +193,23 @@ class ShaderProgram(ShaderModule):
         for module in self.scene.modules:
             header.extend(module.defines() or ())
         try:
-            image, translation, _ = glsl.build(self.fragment, "\n".join(header))
+            # contraction of a*b+c into fma like the ahead-of-time kernels (nvcc's default) and GL drivers; SFB_JIT_FMAD=0
+            # compiles with one rounding per operation, the arithmetic the parity tests hold the translator to
+            image, translation, _ = glsl.build(fragment, "\n".join(header), fmad=os.environ.get("SFB_JIT_FMAD", "1") != "0")
         except (glsl.TranslationError, N.CompileError) as error:
             raise RuntimeError(logger.error(
                 f"ShaderProgram '{self.name}': the fragment shader could not be compiled for the CUDA backend: {error}")) from None
         self.release_runtime()
         self.scene_id = self._runtime_scene = self.scene.cuda.program_load(image, len(translation.samplers))
         self.scene_info = dict(name=f"runtime:{registry.digest(self.fragment)}", extra=list(translation.extra),
-                               samplers=list(translation.samplers), required=len(translation.samplers))
+                               extra_types=list(translation.extra_types), samplers=list(translation.samplers),
+                               required=len(translation.samplers))
         return self
 
     _runtime_scene: Optional[int] = None
+    include_directories: list = Factory(list)
+    """Directories `#include "file"` lines of a run-time compiled fragment are looked up in"""
+    _include_regex = __import__("re").compile(r'^[ \t]*#include[ \t]+"(.+)"[ \t]*$', __import__("re").MULTILINE)
 
     def release_runtime(self) -> None:
         if self._runtime_scene is not None and self.scene.cuda is not None:
@@ -248,7 +275,7 @@ class ShaderProgram(ShaderModule):
     def uniform_block(self, values: dict) -> N.Uniforms:
         w, h = self.scene.resolution
         block = N.Uniforms.defaults(w, h)
-        return pack_uniforms(block, values, self.scene_info["extra"])
+        return pack_uniforms(block, values, self.scene_info["extra"], self.scene_info.get("extra_types"))
 
     def set_uniform(self, name: str, value: Any = None) -> None:
         if self.scene_id is None:

@@ -50,7 +50,5 @@ def native_uniforms(u: G.Uniforms, scene_info: dict):
     n.iLayer = int(getattr(u, "iLayer", 0))
     for key in ("iCameraPosition", "iCameraRight", "iCameraUpward", "iCameraForward", "iCameraZenith"):
         getattr(n, key)[:] = tuple(float(v) for v in getattr(u, key))
-    for slot, name in enumerate(scene_info["extra"]):
-        for k, value in enumerate(np.asarray(u.extra[name], dtype=np.float64).reshape(-1)[:4]):
-            n.extra[slot][k] = float(value)
-    return n
+    from shaderflow_b200.shader import pack_uniforms
+    return pack_uniforms(n, {name: u.extra[name] for name in scene_info["extra"]}, scene_info["extra"], scene_info.get("extra_types"))

@@ -1,6 +1,6 @@
 """Inputs shared by the CPU and GPU tests of the run-time GLSL → CUDA path (shaderflow_b200/glsl, csrc/jit).
 
-    corpus      tests/shaders/{plasma,sdf,bits,textured}.frag — self-contained GLSL (no std-lib call), so the mechanical
+    corpus      tests/shaders/{plasma,sdf,bits,textured,idioms}.frag — self-contained GLSL (no std-lib call), so the mechanical
                 evaluator oracle/glsl_exec.py can execute the very text the translator compiles
     stdlib      tests/shaders/stdlib.frag — calls ShaderFlow's std-lib API group by group; its golden
                 (tests/golden/jit_stdlib.npz) is that text evaluated behind the REFERENCE's own header and include
@@ -16,7 +16,7 @@ from oracle import glsl_exec as X
 from oracle import glsl_np as G
 
 SHADERS = Path(__file__).parent/"shaders"
-CORPUS = ("plasma", "sdf", "bits", "textured")
+CORPUS = ("plasma", "sdf", "bits", "textured", "idioms")
 W, H = 64, 36
 VARYINGS = ("stxy", "glxy", "stuv", "astuv", "gluv", "agluv")
 # what shader.py:190-239 declares in front of every fragment (the names the corpus reads)
