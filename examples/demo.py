@@ -91,6 +91,24 @@ class Dynamics(ShaderScene):
         self.dynamics.target = 0.5*(1 + np.sign(np.sin(2*math.pi*self.time*0.5)))
 
 
+class Video(ShaderScene):
+    """Video as a Texture demo. The reference plays a downloaded clip (examples/basic/demo.py:133-139); here `path` is any
+    .y4m / raw rgb file (or what ffmpeg decodes), by default a synthetic Y4M clip written to the user data directory."""
+    path = None
+
+    def build(self):
+        from shaderflow.video import ShaderVideo
+        path = self.path
+        if path is None:
+            from shaderflow_b200 import synthetic
+            path = shaderflow_b200.directories.user_data_path/"synthetic.y4m"
+            if not path.exists():
+                path.parent.mkdir(parents=True, exist_ok=True)
+                synthetic.write_y4m(path, synthetic.video_frames(640, 360, 60), fps=30)
+        self.video = ShaderVideo(scene=self, path=path)
+        self.shader.fragment = (shaders/"video.frag")
+
+
 class Audio(ShaderScene):
     """Basic audio processing (the reference opens a soundcard recorder; here a clip is loaded)"""
     def build(self):

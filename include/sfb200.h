@@ -304,6 +304,20 @@ int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int back
                         int width, int height, int ssaa, int* rows_per_thread, int* window_rows);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Video frames as textures — replaces ShaderVideo.update's host-side work (video.py:57-66: np.flip, a C-order copy,
+ * texture.write of an rgb24 frame ffmpeg decoded). frame_dev holds ONE frame in the file's own layout (rows top to
+ * bottom when top_down, as decoders and Y4M deliver them); the kernel flips it to GL's bottom-row-first order,
+ * converts planar YUV to RGB (BT.601 limited range; SFB_VIDEO_FULL_RANGE = JPEG range) and writes the texture's
+ * storage (8-bit, 3 or 4 components, width x height). sfb_video_frame_bytes = size of one frame (0: unknown format). */
+enum {
+    SFB_VIDEO_RGB24 = 0, SFB_VIDEO_RGBA32 = 1,
+    SFB_VIDEO_YUV420P = 2, SFB_VIDEO_YUV422P = 3, SFB_VIDEO_YUV444P = 4,   /* planar Y, U, V (I420 order) */
+    SFB_VIDEO_FULL_RANGE = 0x100,                                          /* or'ed to a YUV format */
+};
+size_t sfb_video_frame_bytes(int format, int width, int height);
+int sfb_video_frame(sfb_ctx* ctx, const void* frame_dev, int format, int width, int height, int top_down, sfb_tex* texture);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Run-time compiled programs — the other half of ShaderProgram.compile (shader.py:313-349 hands ANY fragment text to
  * the GL driver). A fragment this library has no ahead-of-time kernel for is translated GLSL → CUDA by the host side
  * (shaderflow_b200/glsl) and compiled here:

@@ -26,6 +26,7 @@ SCALARS = 5
 SCENE_COUNT = 17
 SCENE_PROGRAM_BASE = 1000
 JIT_FMAD = 1
+VIDEO_RGB24, VIDEO_RGBA32, VIDEO_YUV420P, VIDEO_YUV422P, VIDEO_YUV444P, VIDEO_FULL_RANGE = 0, 1, 2, 3, 4, 0x100
 SCALAR_VOLUME, SCALAR_VOLUME_INTEGRAL, SCALAR_STD, SCALAR_VOLUME_TARGET, SCALAR_STD_TARGET = range(5)
 
 
@@ -134,6 +135,8 @@ _PROTOTYPES = dict(
     sfb_sink_finish=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     sfb_sink_abort=(c_int, [c_void_p]),
     sfb_sink_close=(c_int, [c_void_p]),
+    sfb_video_frame_bytes=(c_size_t, [c_int, c_int, c_int]),
+    sfb_video_frame=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_jit_compile=(c_int, [c_char_p, POINTER(c_char_p), POINTER(c_char_p), c_int, c_int, POINTER(c_void_p), POINTER(c_size_t),
                              POINTER(c_void_p)]),
     sfb_jit_free=(None, [c_void_p]),
@@ -175,6 +178,10 @@ class CompileError(RuntimeError):
     def __init__(self, message: str, log: str):
         super().__init__(message + ("\n" + log if log else ""))
         self.log = log
+
+
+def video_frame_bytes(fmt: int, width: int, height: int) -> int:
+    return int(lib().sfb_video_frame_bytes(fmt, width, height))
 
 
 def jit_compile(source: str, headers: dict[str, str], flags: int = 0) -> tuple[bytes, str]:
@@ -479,6 +486,10 @@ class Context:
     def pcm_ingest(self, raw, n_frames: int, channels: int, fmt: int, planar, clip_samples: int, offset: int) -> None:
         """Interleaved file samples (device bytes) → rows [offset, offset+n_frames) of the planar float32 clip"""
         check(lib().sfb_pcm_ingest(self.handle, _ptr(raw), n_frames, channels, fmt, _ptr(planar), clip_samples, offset))
+
+    def video_frame(self, frame, fmt: int, width: int, height: int, top_down: bool, texture: "Texture") -> None:
+        """One decoded frame (device bytes in the file's layout) → the texture's storage, flipped / converted on the GPU"""
+        check(lib().sfb_video_frame(self.handle, _ptr(frame), fmt, width, height, int(top_down), texture.handle))
 
     def program_load(self, image: bytes, n_samplers: int) -> int:
         """SASS image of a run-time compiled program → scene id (>= SCENE_PROGRAM_BASE) for the render_* calls"""

@@ -34,3 +34,37 @@ def background(width: int = 1920, height: int = 1080, seed: int = 1) -> np.ndarr
                     0.5 + 0.5*np.cos(9.0*(x - 0.5)*(y - 0.5) + 2.0)], -1)
     img += rng.uniform(-0.08, 0.08, img.shape)
     return (np.clip(img, 0, 1)*255).round().astype(np.uint8)
+
+
+def video_frames(width: int = 320, height: int = 180, frames: int = 30, seed: int = 3) -> np.ndarray:
+    """Deterministic rgb24 test clip (frames, height, width, 3), top row first: the background drifting sideways with a
+    frame counter stripe, so every frame and both orientations are distinguishable"""
+    base = background(width, height, seed)
+    out = np.empty((frames, height, width, 3), np.uint8)
+    for k in range(frames):
+        out[k] = np.roll(base, 7*k, axis=1)
+        out[k, :max(2, height//16), :(k + 1)*width//max(frames, 1)] = (255, 255 - 8*k % 256, 8*k % 256)
+    return out
+
+
+def write_y4m(path, rgb: np.ndarray, fps: int = 30, colorspace: str = "420jpeg") -> None:
+    """rgb24 frames (frames, H, W, 3, top row first) → a YUV4MPEG2 file: BT.601 limited range, chroma = box mean of the
+    samples it covers (even W and H for 420 / 422). The inverse of what sfb_video_frame undoes, up to the chroma loss."""
+    rgb = np.asarray(rgb, np.float32)
+    r, g, b = rgb[..., 0], rgb[..., 1], rgb[..., 2]
+    y = 16.0 + 0.256788*r + 0.504129*g + 0.097906*b
+    u = 128.0 - 0.148223*r - 0.290993*g + 0.439216*b
+    v = 128.0 + 0.439216*r - 0.367788*g - 0.071427*b
+    if colorspace.startswith("420"):
+        u = u.reshape(u.shape[0], u.shape[1]//2, 2, u.shape[2]//2, 2).mean(axis=(2, 4))
+        v = v.reshape(v.shape[0], v.shape[1]//2, 2, v.shape[2]//2, 2).mean(axis=(2, 4))
+    elif colorspace.startswith("422"):
+        u = u.reshape(u.shape[0], u.shape[1], u.shape[2]//2, 2).mean(axis=3)
+        v = v.reshape(v.shape[0], v.shape[1], v.shape[2]//2, 2).mean(axis=3)
+    planes = [np.clip(np.rint(p), 0, 255).astype(np.uint8) for p in (y, u, v)]
+    with open(path, "wb") as f:
+        f.write(f"YUV4MPEG2 W{rgb.shape[2]} H{rgb.shape[1]} F{fps}:1 Ip A1:1 C{colorspace}\n".encode())
+        for k in range(rgb.shape[0]):
+            f.write(b"FRAME\n")
+            for p in planes:
+                f.write(p[k].tobytes())
