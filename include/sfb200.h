@@ -304,6 +304,22 @@ int sfb_visualizer_plan(const sfb_uniforms* uniforms, int background_w, int back
                         int width, int height, int ssaa, int* rows_per_thread, int* window_rows);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* FLAC streams — audio files without an ffmpeg child (the reference decodes every compressed file through
+ * `ffmpeg -f f32le`, ffmpeg.py:1240-1333). Host-side: the bit stream is serial work, no GPU and no sfb_ctx involved.
+ *   sfb_flac_info_get  STREAMINFO of a stream held in memory (an ID3v2 tag in front is skipped).
+ *   sfb_flac_decode    every frame → interleaved samples [frame][channel], right-justified int32 (a 16-bit stream
+ *                      yields values in [-32768, 32767]); pcm NULL = count only. All CRC-8 / CRC-16 are verified
+ *                      (SFB_EINVAL on a mismatch or malformed stream); md5 is for the caller to check. */
+typedef struct sfb_flac_info {
+    int32_t samplerate, channels, bits_per_sample, has_md5;
+    int64_t total_samples;                  /* per channel; 0 = not recorded in the stream */
+    int32_t min_block, max_block;
+    uint8_t md5[16];                        /* of the interleaved little-endian samples, ceil(bits/8) bytes each */
+} sfb_flac_info;
+int sfb_flac_info_get(const void* data, size_t bytes, sfb_flac_info* info);
+int sfb_flac_decode(const void* data, size_t bytes, int32_t* pcm, int64_t capacity_frames, int64_t* decoded_frames);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Video frames as textures — replaces ShaderVideo.update's host-side work (video.py:57-66: np.flip, a C-order copy,
  * texture.write of an rgb24 frame ffmpeg decoded). frame_dev holds ONE frame in the file's own layout (rows top to
  * bottom when top_down, as decoders and Y4M deliver them); the kernel flips it to GL's bottom-row-first order,

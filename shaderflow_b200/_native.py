@@ -60,6 +60,12 @@ class Uniforms(C.Structure):
         return u
 
 
+class FlacInfo(C.Structure):
+    """struct sfb_flac_info"""
+    _fields_ = [("samplerate", c_int32), ("channels", c_int32), ("bits_per_sample", c_int32), ("has_md5", c_int32),
+                ("total_samples", c_int64), ("min_block", c_int32), ("max_block", c_int32), ("md5", C.c_uint8*16)]
+
+
 class DynamicsParams(C.Structure):
     _fields_ = [("frequency", c_double), ("zeta", c_double), ("response", c_double), ("precision", c_double)]
 
@@ -135,6 +141,8 @@ _PROTOTYPES = dict(
     sfb_sink_finish=(c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     sfb_sink_abort=(c_int, [c_void_p]),
     sfb_sink_close=(c_int, [c_void_p]),
+    sfb_flac_info_get=(c_int, [c_void_p, c_size_t, POINTER(FlacInfo)]),
+    sfb_flac_decode=(c_int, [c_void_p, c_size_t, c_void_p, c_int64, POINTER(c_int64)]),
     sfb_video_frame_bytes=(c_size_t, [c_int, c_int, c_int]),
     sfb_video_frame=(c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     sfb_jit_compile=(c_int, [c_char_p, POINTER(c_char_p), POINTER(c_char_p), c_int, c_int, POINTER(c_void_p), POINTER(c_size_t),
@@ -178,6 +186,21 @@ class CompileError(RuntimeError):
     def __init__(self, message: str, log: str):
         super().__init__(message + ("\n" + log if log else ""))
         self.log = log
+
+
+def flac_decode(data) -> tuple[FlacInfo, "np.ndarray"]:
+    """A FLAC stream in memory (bytes / uint8 array) → (STREAMINFO, samples int32 [frames][channels], right-justified)"""
+    import numpy as np
+    raw = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+    info, frames = FlacInfo(), c_int64()
+    check(lib().sfb_flac_info_get(raw.ctypes.data, raw.size, byref(info)))
+    total = int(info.total_samples)
+    if total == 0:                                             # not recorded: walk the frames once to count
+        check(lib().sfb_flac_decode(raw.ctypes.data, raw.size, None, 0, byref(frames)))
+        total = frames.value
+    pcm = np.empty((total, info.channels), dtype=np.int32)
+    check(lib().sfb_flac_decode(raw.ctypes.data, raw.size, pcm.ctypes.data, total, byref(frames)))
+    return info, pcm[:frames.value]
 
 
 def video_frame_bytes(fmt: int, width: int, height: int) -> int:

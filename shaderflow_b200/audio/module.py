@@ -36,12 +36,15 @@ class AudioMode(Enum):
 
 
 def read_audio_file(path: Path) -> tuple[np.ndarray, int]:
-    """→ (pcm float32 (channels, samples), samplerate). RIFF/WAVE natively (audio/reader.py), anything else
+    """→ (pcm float32 (channels, samples), samplerate). RIFF/WAVE and FLAC natively (audio/reader.py), anything else
     through ffmpeg when a binary exists"""
     path = Path(path)
     if path.suffix.lower() in (".wav", ".wave", ".rf64"):
         from shaderflow_b200.audio.reader import read_wav
         return read_wav(path)
+    if path.suffix.lower() in (".flac", ".fla"):
+        from shaderflow_b200.audio.reader import read_flac
+        return read_flac(path)
     ffmpeg, ffprobe = shutil.which("ffmpeg"), shutil.which("ffprobe")
     if not (ffmpeg and ffprobe):
         raise RuntimeError(f"Decoding '{path}' needs ffmpeg/ffprobe on PATH; load WAV files or call load(pcm, samplerate)")

@@ -13,8 +13,8 @@ there. RIFF/WAVE (and RF64) files are parsed here and need no decoder at all:
 
 `read_wav` is the host-side equivalent (same arithmetic in numpy) for the API surface that hands out numpy
 arrays (`BrokenAudio.clip`, `get_last_n_samples`). Compressed formats still go through ffmpeg when a binary
-exists (audio/module.py: read_audio_file); FLAC has no native decoder here — no FLAC stream or encoder exists in
-the build image to pin one against."""
+exists (audio/module.py: read_audio_file). FLAC streams are decoded natively on the host (`read_flac`, csrc/flac.cu —
+a serial bit stream is no work for a GPU) with every frame CRC and the stream's MD5 checked."""
 from __future__ import annotations
 
 import struct
@@ -121,6 +121,23 @@ def read_wav(path) -> tuple[np.ndarray, int]:
     info = parse_wav(path)
     raw = np.fromfile(info.path, dtype=np.uint8, offset=info.data_offset, count=info.frames*info.block)
     return np.ascontiguousarray(decode_pcm(raw, info.format, info.channels).T), info.samplerate
+
+
+def read_flac(path, verify: bool = True) -> tuple[np.ndarray, int]:
+    """→ (pcm float32 (channels, samples), samplerate). The stream is decoded on the host by csrc/flac.cu (every frame's
+    CRC checked there); the MD5 of STREAMINFO, when the encoder recorded one, is checked here against the decoded
+    samples. Conversion to float as libswresample does for s16 / s32 sources: x / 2^(bits−1)."""
+    import hashlib
+    data = np.fromfile(path, dtype=np.uint8)
+    info, pcm = N.flac_decode(data)
+    bits = int(info.bits_per_sample)
+    if verify and info.has_md5:
+        width = (bits + 7)//8
+        packed = pcm.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :width]          # little-endian, sign-extended to whole bytes
+        if hashlib.md5(np.ascontiguousarray(packed).tobytes()).digest() != bytes(info.md5):
+            raise ValueError(f"'{path}': the decoded samples do not match the stream's MD5 signature")
+    scale = np.float32(1.0/float(1 << (bits - 1)))
+    return np.ascontiguousarray((pcm.astype(np.float32)*scale).T), int(info.samplerate)
 
 
 def upload_wav(ctx: "N.Context", info: WavInfo, device: int, staging_bytes: int = 32 << 20):

@@ -19,7 +19,7 @@ PACKAGE = Path(__file__).resolve().parent
 CSRC = PACKAGE/"csrc"
 OBJ = CSRC/"build"
 LIBRARY = PACKAGE/"libsfb200.so"
-UNITS = ("core.cu", "audio.cu", "render.cu", "render_screen.cu", "render_frame.cu", "render_lanes.cu", "visualizer_tiled_1.cu", "visualizer_tiled_2.cu", "visualizer_tiled_3.cu", "visualizer_tiled_4.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu", "ingest.cu", "jit.cu", "video.cu")
+UNITS = ("core.cu", "audio.cu", "render.cu", "render_screen.cu", "render_frame.cu", "render_lanes.cu", "visualizer_tiled_1.cu", "visualizer_tiled_2.cu", "visualizer_tiled_3.cu", "visualizer_tiled_4.cu", "visualizer_rows.cu", "piano.cu", "pipe.cu", "sink.cu", "ingest.cu", "jit.cu", "video.cu", "flac.cu")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -60,3 +60,25 @@ def test_export_from_a_wav_file_equals_the_numpy_clip_export(tmp_path, fps, seco
     assert len(a) == len(b) == 320*180*3*round(seconds*fps)
     assert a == b
     assert torch.equal(from_file.audio.clip_device, from_array.audio.clip_device)
+
+
+def test_export_from_a_flac_file_equals_the_numpy_clip_export(tmp_path):
+    """The same export from a FLAC stream (host decode, csrc/flac.cu; written by the independent test encoder): the
+    frames are those of the clip loaded as an array"""
+    from shaderflow_b200 import synthetic
+    from examples.demo import Visualizer, synthetic_background
+    from tests.flac_writer import write_flac
+    quantised = np.round(synthetic.noise(0.3)*32767).astype(np.int64)
+    (tmp_path/"clip.flac").write_bytes(write_flac(quantised.T, blocksize=4096, subframe="fixed2", stereo="mid_side"))
+    Visualizer.background = synthetic_background(240, 135)
+    try:
+        flags = dict(width=320, height=180, ssaa=2, subsample=2, fps=60.0, time=0.3, output=bytes)
+        from_file = Visualizer(device=0); from_file.initialize()
+        from_file.audio.file = tmp_path/"clip.flac"
+        a = from_file.main(**flags)
+        from_array = Visualizer(device=0); from_array.initialize()
+        from_array.audio.load((quantised/32768).astype(np.float32), 44100)
+        b = from_array.main(**flags)
+    finally:
+        Visualizer.background = None
+    assert len(a) == 320*180*3*18 and a == b
