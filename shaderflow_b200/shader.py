@@ -21,6 +21,7 @@ from shaderflow_b200.texture import ShaderTexture, TextureBox
 from shaderflow_b200.variable import FlatVariable, InVariable, OutVariable, ShaderVariable
 
 _FIXED_FIELDS = {name for name, _ in N.Uniforms._fields_} - {"extra"}
+_IMAGES: dict = {}           # SASS images of run-time compiled programs by digest of their CUDA source (per process)
 DEFAULT_FRAGMENT = "// sfb200: scene=default"
 FINAL_FRAGMENT = "// sfb200: scene=final"
 
@@ -160,6 +161,7 @@ class ShaderProgram(ShaderModule):
         name = registry.resolve(self._fragment)
         if name is None:
             return self._compile_runtime()
+        self.release_runtime()
         self.scene_id = N.scene_lookup(name)
         self.scene_info = N.scene_info(self.scene_id)
         return self
@@ -170,6 +172,7 @@ class ShaderProgram(ShaderModule):
         what `_build_shader` assembles (shader.py:190-239): every pipeline variable's declaration and the modules'
         defines (texture aliases and accessors); the std-lib (shaderflow.glsl, camera.glsl) comes from
         csrc/jit/shaderflow_rt.cuh. Raises RuntimeError with the translator's / compiler's diagnostics."""
+        import hashlib
         import os
         from shaderflow_b200 import glsl
         fragment = self.fragment
@@ -192,29 +195,52 @@ class ShaderProgram(ShaderModule):
                 header.append(variable.declaration)
         for module in self.scene.modules:
             header.extend(module.defines() or ())
+        # contraction of a*b+c into fma like the ahead-of-time kernels (nvcc's default) and GL drivers; SFB_JIT_FMAD=0
+        # compiles with one rounding per operation, the arithmetic the parity tests hold the translator to
+        fmad = os.environ.get("SFB_JIT_FMAD", "1") != "0"
         try:
-            # contraction of a*b+c into fma like the ahead-of-time kernels (nvcc's default) and GL drivers; SFB_JIT_FMAD=0
-            # compiles with one rounding per operation, the arithmetic the parity tests hold the translator to
-            image, translation, _ = glsl.build(fragment, "\n".join(header), fmad=os.environ.get("SFB_JIT_FMAD", "1") != "0")
+            translation = glsl.translate(fragment, "\n".join(header))
+            source = glsl.program(translation)
+            key = hashlib.sha1((source + f"|fmad={int(fmad)}|{N.LIBRARY.stat().st_mtime_ns}").encode()).hexdigest()
+            if key == self._runtime_key and self._runtime_scene is not None:
+                return self                                    # main() compiles every export: same text, same program
+            image = _IMAGES.get(key)
+            cache = os.environ.get("SFB_JIT_CACHE")            # optional on-disk cache of SASS images (a directory)
+            if image is None and cache and (Path(cache)/f"{key}.cubin").is_file():
+                image = (Path(cache)/f"{key}.cubin").read_bytes()
+            if image is None:
+                image, _ = N.jit_compile(source, glsl.headers(), N.JIT_FMAD if fmad else 0)
+                if cache:
+                    Path(cache).mkdir(parents=True, exist_ok=True)
+                    (Path(cache)/f"{key}.cubin").write_bytes(image)
+            _IMAGES[key] = image
         except (glsl.TranslationError, N.CompileError) as error:
             raise RuntimeError(logger.error(
                 f"ShaderProgram '{self.name}': the fragment shader could not be compiled for the CUDA backend: {error}")) from None
         self.release_runtime()
         self.scene_id = self._runtime_scene = self.scene.cuda.program_load(image, len(translation.samplers))
+        self._runtime_key = key
         self.scene_info = dict(name=f"runtime:{registry.digest(self.fragment)}", extra=list(translation.extra),
                                extra_types=list(translation.extra_types), samplers=list(translation.samplers),
                                required=len(translation.samplers))
         return self
 
+    _runtime_key: Optional[str] = None
     _runtime_scene: Optional[int] = None
     include_directories: list = Factory(list)
     """Directories `#include "file"` lines of a run-time compiled fragment are looked up in"""
     _include_regex = __import__("re").compile(r'^[ \t]*#include[ \t]+"(.+)"[ \t]*$', __import__("re").MULTILINE)
 
+    def destroy(self) -> None:
+        try:
+            self.release_runtime()
+        except Exception:
+            pass                                   # the context may already be gone at interpreter exit
+
     def release_runtime(self) -> None:
         if self._runtime_scene is not None and self.scene.cuda is not None:
             self.scene.cuda.program_unload(self._runtime_scene)
-        self._runtime_scene = None
+        self._runtime_scene = self._runtime_key = None
 
     # -- uniforms ------------------------------------------------------------------------------
     _plan: Any = None
