@@ -51,6 +51,7 @@ constexpr int VR_ROWS = 4;             // texel rows interpolated per tap: cover
 constexpr int VR_HG = 21;              // vertical (hinge) groups: 0 = rays 0°/180°, 1-10 = rays 45°/135°, 11-20 = rays 225°/315°
 constexpr int VR_MAXQ = 6;             // phase 1 walks at most 4*VR_MAXQ texel rows
 constexpr int VR_VTAPS = 21;           // taps with dx = 0: rays 90°, 270°, the undisplaced tap
+constexpr int VR_NI_MAX = 12;          // phase 2: texel columns the merged horizontal weights of a fragment column may span
 
 struct RowsTaps {
     float hdx[20];                     // phase 2: dx of ray 0 (10 walks), then ray 180°
@@ -173,6 +174,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     float2* bb = reinterpret_cast<float2*>(vr_smem + sizeof(float4)*VR_WIN_W*win_h);     // [win_h][64] (b, b'-b)
     float4* tblH = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][VR_HG][J] hinge weights + row offset
     float4* tblM = tblH + VR_GROUPS*VR_HG*J;                                             // [4][VR_MAXQ][J] merged weights of 4 texel rows
+    float* wx = reinterpret_cast<float*>(tblM + VR_GROUPS*VR_MAXQ*J);                    // [VR_NI_MAX][64] phase 2: merged horizontal weights
     __shared__ float red[2][VR_THREADS/32];
     __shared__ float cyS[VR_GROUPS][J];
     __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
@@ -281,6 +283,26 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
     }
+    // merged horizontal weights of the dy = 0 taps (phase 2): the 20 taps of rays 0° (counted twice) and 180° read the
+    // same 4 texel rows, so their horizontal lerps add up to ONE weighted sum over the ni texel columns they can touch,
+    // wx[k][column] = sum over the taps of weight * hat(px_tap - texel k). The weights depend on the fragment column
+    // only: each column's 4 threads (one per row group) compute them once per CTA.
+    const int ni = int(2.0f*scale*1.0001f) + 3;                    // warp-uniform: texel columns floor(cx - s) .. floor(cx + s) + 1
+    const bool merged_x = window_ok && ni <= VR_NI_MAX && !(VP.debug & 4);
+    const float cxl = tapx - float(x0);                            // tile-local column position, >= 2 by construction of x0
+    const int ix0 = int(floorf(cxl - scale*1.0001f));
+    if (merged_x) {
+        for (int k = ty; k < ni; k += VR_GROUPS) {
+            const float at = float(ix0 + k);
+            float w = 0.0f;
+            #pragma unroll 5
+            for (int t = 0; t < 10; t++) {
+                w += 2.0f*fmaxf(1.0f - fabsf(fmaf(c_rows.hdx[t], scale, cxl) - at), 0.0f);
+                w += fmaxf(1.0f - fabsf(fmaf(c_rows.hdx[10 + t], scale, cxl) - at), 0.0f);
+            }
+            wx[k*VR_COLS + tx] = w;
+        }
+    }
 
     // ---- B2. widen the window into pre-differenced pair records -------------------------------------
     if (window_ok) {
@@ -387,7 +409,29 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         }
         const float4* T = tblH + ty*(VR_HG*J);
         // phase 2: the dy = 0 taps; ray 0 is weighted twice
-        {
+        if (merged_x) {
+            // one pass over the ni texel columns with the merged weights: per column and texel row one 8-byte and one
+            // 4-byte load (r, g, b of the record; the differences are not needed) instead of 20 two-texel gathers
+            const float4 e0 = T[0];
+            const unsigned int base8 = __float_as_uint(e0.w) + (0x4B000000u << 3) + ((unsigned int)ix0 << 3);
+            const char* pr = rgB + 2u*base8;
+            const char* pb = bbB + base8;
+            const float* wk = wx + tx;
+            float H[VR_ROWS][3];
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS; r++) { H[r][0] = 0.0f; H[r][1] = 0.0f; H[r][2] = 0.0f; }
+            #pragma unroll 3
+            for (int k = 0; k < ni; k++, pr += 16, pb += 8, wk += VR_COLS) {
+                const float w = *wk;
+                #pragma unroll
+                for (int r = 0; r < VR_ROWS; r++) {
+                    const float2 q = *reinterpret_cast<const float2*>(pr + r*(VR_WIN_W*16));
+                    const float b = *reinterpret_cast<const float*>(pb + r*(VR_WIN_W*8));
+                    H[r][0] = fmaf(w, q.x, H[r][0]); H[r][1] = fmaf(w, q.y, H[r][1]); H[r][2] = fmaf(w, b, H[r][2]);
+                }
+            }
+            apply(T, e0, H);
+        } else {
             const float4 e0 = T[0];
             const unsigned int rowoff = __float_as_uint(e0.w);
             float H[VR_ROWS][3];
@@ -563,7 +607,7 @@ template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP
     static bool configured[64] = {};                      // the attribute is per device
     int device = 0;
     if (cudaError_t e = cudaGetDevice(&device); e != cudaSuccess) return e;
-    const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J;
+    const size_t table = sizeof(float4)*VR_GROUPS*(VR_HG + VR_MAXQ)*J + sizeof(float)*VR_NI_MAX*VR_COLS;
     const size_t epilogue = sizeof(float4)*J*VR_THREADS + size_t(VR_GROUPS*J)*VR_COLS*3;   // stash + rgb24 staging
     if (device >= 64 || !configured[device]) {
         size_t most = size_t(VR_TEXEL_BYTES)*WW*vr_max_h(WW) + table;
