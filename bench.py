@@ -497,7 +497,7 @@ def run_b200(args, rank: int, world: int, local: int) -> None:
     try: limiter = json.loads((ROOT/"profiles"/"ncu_summary.json").read_text())["frame_kernel_visualizer"].get("limiter", {})
     except Exception: pass
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved/peak, traffic=traffic,
-                    kernel="visualizer_rows_kernel<2, 8> (+ visualizer_frame_consts_kernel, 1 thread)", kernel_ms=kernel_avg_ms,
+                    kernel="visualizer_rows_kernel<2, 8, 64>", kernel_ms=kernel_avg_ms,
                     launches_timed=len(kernel_ms),
                     algorithmic_bytes_per_launch=algorithmic, peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                     note="not HBM-bound: 91 bilinear taps per fragment are served from a shared-memory window, so the kernel is "

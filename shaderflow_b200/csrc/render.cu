@@ -94,71 +94,84 @@ __global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ Fina
 // The reference's DEFAULT export geometry — ssaa 1 (iScreen at the final resolution) with subsample 2 (scene.py:526-528)
 // — in its own kernel: the four taps of a pixel sit a quarter texel around its centre, so they read the 3 x 3 texels
 // around it and their sum is a separable 3 x 3 filter with weights ((1-a0), a0 + (1-a1), a1) per axis, a0 / a1 being
-// the fractional tap positions exactly as final.glsl's float32 arithmetic produces them. A CTA of 32 x 8 pixels
-// widens its 34 x 10 texels once into shared memory (each texel serves 9 pixels) instead of loading and widening 16
-// texels per pixel. A thread whose taps do not land on the expected texels (never, short of NaN) takes the generic path.
+// the fractional tap positions exactly as final.glsl's float32 arithmetic produces them. A CTA of 32 x 32 pixels (four
+// pixel rows per thread) widens its 34 x 34 texels once into shared memory — each texel serves 9 pixels, one tile load
+// and one barrier per 1024 pixels — instead of loading and widening 16 texels per pixel. A thread whose taps do not
+// land on the expected texels (never, short of NaN) takes the generic path.
+constexpr int FINAL_TILE_H = 32;             // pixel rows per CTA: 4 adjacent rows per thread, one tile load and one barrier for 1024 pixels
 __global__ void __launch_bounds__(256) final_half_step_kernel(const __grid_constant__ FinalParams P) {
-    __shared__ float4 tile[10][34];
-    __shared__ unsigned int stage[8][32];
+    __shared__ float4 tile[FINAL_TILE_H + 2][34];
+    __shared__ unsigned int stage[8][4][24];
     const int tid = threadIdx.y*32 + threadIdx.x;
-    const int x0 = blockIdx.x*32, y0 = blockIdx.y*8;
-    for (int t = tid; t < 340; t += 256) {
+    const int x0 = blockIdx.x*32, y0 = blockIdx.y*FINAL_TILE_H;
+    for (int t = tid; t < (FINAL_TILE_H + 2)*34; t += 256) {
         const int r = t/34, c = t - r*34;
         const int gx = min(max(x0 - 1 + c, 0), P.Ws - 1), gy = min(max(y0 - 1 + r, 0), P.Hs - 1);
         const vec3 v = widen3(__ldg(reinterpret_cast<const unsigned int*>(P.screen) + size_t(gy)*size_t(P.Ws) + size_t(gx)));
         tile[r][c] = make_float4(v.x, v.y, v.z, 0.0f);
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool inside = (x < P.W) && (y < P.H);
-    unsigned int r8 = 0, g8 = 0, b8 = 0;
-    if (inside) {
-        const vec2 astuv = mk2(float((double(x) + 0.5)*P.inv_W), float((double(y) + 0.5)*P.inv_H));
-        const vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
-        const vec2 corner = astuv - (pixel_size/2.0f);
-        const vec2 step = pixel_size/2.0f;
-        const vec2 origin = corner + step/2.0f;
-        // tap coordinates of final.glsl:17-28 for x, y = 0, 1, then texture()'s texel position u*W - 0.5
-        const float ub0 = (origin.x + step.x*0.0f)*float(P.Ws) - 0.5f, ub1 = (origin.x + step.x*1.0f)*float(P.Ws) - 0.5f;
-        const float vb0 = (origin.y + step.y*0.0f)*float(P.Hs) - 0.5f, vb1 = (origin.y + step.y*1.0f)*float(P.Hs) - 0.5f;
-        const float fx0 = floorf(ub0), fx1 = floorf(ub1), fy0 = floorf(vb0), fy1 = floorf(vb1);
-        vec3 rgb;
-        if (int(fx0) == x - 1 && int(fx1) == x && int(fy0) == y - 1 && int(fy1) == y) {
-            const float a0 = ub0 - fx0, a1 = ub1 - fx1, b0 = vb0 - fy0, b1 = vb1 - fy1;
-            const float wx[3] = {1.0f - a0, a0 + (1.0f - a1), a1};
-            const float wy[3] = {1.0f - b0, b0 + (1.0f - b1), b1};
-            vec3 acc = mk3(0.0f);
-            #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const float4 t0 = tile[threadIdx.y + r][threadIdx.x], t1 = tile[threadIdx.y + r][threadIdx.x + 1], t2 = tile[threadIdx.y + r][threadIdx.x + 2];
-                const vec3 h = mk3(wx[0]*t0.x + wx[1]*t1.x + wx[2]*t2.x, wx[0]*t0.y + wx[1]*t1.y + wx[2]*t2.y, wx[0]*t0.z + wx[1]*t1.z + wx[2]*t2.z);
-                acc = acc + h*wy[r];
+    const int x = x0 + threadIdx.x, ly0 = threadIdx.y*4;
+    const vec2 pixel_size = mk2(1.0f/float(P.W), 1.0f/float(P.H));
+    const vec2 step = pixel_size/2.0f;
+    // the column's part of final.glsl:17-28: tap coordinates for x = 0, 1, then texture()'s texel position u*W - 0.5
+    const float astu = float((double(x) + 0.5)*P.inv_W);
+    const float originx = (astu - pixel_size.x/2.0f) + step.x/2.0f;
+    const float ub0 = (originx + step.x*0.0f)*float(P.Ws) - 0.5f, ub1 = (originx + step.x*1.0f)*float(P.Ws) - 0.5f;
+    const float fx0 = floorf(ub0), fx1 = floorf(ub1);
+    const bool column_ok = int(fx0) == x - 1 && int(fx1) == x;
+    const float a0 = ub0 - fx0, a1 = ub1 - fx1;
+    const float wx[3] = {1.0f - a0, a0 + (1.0f - a1), a1};
+    // horizontal 3-tap sums of the 6 texel rows the thread's 4 pixel rows read (each serves up to 3 of them)
+    vec3 h[6];
+    #pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const float4 t0 = tile[ly0 + r][threadIdx.x], t1 = tile[ly0 + r][threadIdx.x + 1], t2 = tile[ly0 + r][threadIdx.x + 2];
+        h[r] = mk3(wx[0]*t0.x + wx[1]*t1.x + wx[2]*t2.x, wx[0]*t0.y + wx[1]*t1.y + wx[2]*t2.y, wx[0]*t0.z + wx[1]*t1.z + wx[2]*t2.z);
+    }
+    const bool words = (P.comps == 3) && (P.W % 4 == 0) && (x0 + 32 <= P.W);
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int y = y0 + ly0 + j;
+        const bool inside = (x < P.W) && (y < P.H);
+        unsigned int r8 = 0, g8 = 0, b8 = 0;
+        if (inside) {
+            const float astv = float((double(y) + 0.5)*P.inv_H);
+            const float originy = (astv - pixel_size.y/2.0f) + step.y/2.0f;
+            const float vb0 = (originy + step.y*0.0f)*float(P.Hs) - 0.5f, vb1 = (originy + step.y*1.0f)*float(P.Hs) - 0.5f;
+            const float fy0 = floorf(vb0), fy1 = floorf(vb1);
+            vec3 rgb;
+            if (column_ok && int(fy0) == y - 1 && int(fy1) == y) {
+                const float b0 = vb0 - fy0, b1 = vb1 - fy1;
+                rgb = ((mk3(0.0f) + h[j]*(1.0f - b0)) + h[j + 1]*(b0 + (1.0f - b1))) + h[j + 2]*b1;
+                rgb = rgb*((1.0f/255.0f)/4.0f);
+            } else {
+                const vec2 origin = mk2(originx, originy);
+                vec3 acc = mk3(0.0f);
+                for (int sx = 0; sx < 2; sx++)
+                    for (int sy = 0; sy < 2; sy++)
+                        acc = acc + screen_bilinear255(P, origin + step*mk2(float(sx), float(sy)));
+                rgb = acc*((1.0f/255.0f)/4.0f);
             }
-            rgb = acc*((1.0f/255.0f)/4.0f);
-        } else {
-            vec3 acc = mk3(0.0f);
-            for (int sx = 0; sx < 2; sx++)
-                for (int sy = 0; sy < 2; sy++)
-                    acc = acc + screen_bilinear255(P, origin + step*mk2(float(sx), float(sy)));
-            rgb = acc*((1.0f/255.0f)/4.0f);
+            r8 = to_unorm8(rgb.x); g8 = to_unorm8(rgb.y); b8 = to_unorm8(rgb.z);
         }
-        r8 = to_unorm8(rgb.x); g8 = to_unorm8(rgb.y); b8 = to_unorm8(rgb.z);
+        if (P.comps == 4) {
+            if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
+        } else if (!words) {
+            if (inside) { unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r8; p[1] = g8; p[2] = b8; }
+        } else {
+            unsigned char* row = reinterpret_cast<unsigned char*>(stage[threadIdx.y][j]);
+            row[threadIdx.x*3 + 0] = r8; row[threadIdx.x*3 + 1] = g8; row[threadIdx.x*3 + 2] = b8;
+        }
     }
-    if (P.comps == 4) {
-        if (inside) reinterpret_cast<uchar4*>(P.dst)[size_t(y)*size_t(P.W) + size_t(x)] = make_uchar4(r8, g8, b8, 255);
-        return;
-    }
-    const bool words = (P.W % 4 == 0) && (x0 + 32 <= P.W);
-    if (!words) {
-        if (inside) { unsigned char* p = P.dst + (size_t(y)*size_t(P.W) + size_t(x))*3; p[0] = r8; p[1] = g8; p[2] = b8; }
-        return;
-    }
-    unsigned char* row = reinterpret_cast<unsigned char*>(stage[threadIdx.y]);
-    row[threadIdx.x*3 + 0] = r8; row[threadIdx.x*3 + 1] = g8; row[threadIdx.x*3 + 2] = b8;
-    __syncwarp();
-    if (threadIdx.x < 24 && y < P.H) {
-        unsigned int* out = reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(x0))*3);
-        out[threadIdx.x] = stage[threadIdx.y][threadIdx.x];
+    if (words) {
+        // a warp owns 4 pixel rows: their 4 x 96 bytes leave as 96 words through the warp's staging rows
+        __syncwarp();
+        for (int w = threadIdx.x; w < 96; w += 32) {
+            const int j = w/24, c = w - j*24, y = y0 + ly0 + j;
+            if (y < P.H)
+                reinterpret_cast<unsigned int*>(P.dst + (size_t(y)*size_t(P.W) + size_t(x0))*3)[c] = stage[threadIdx.y][j][c];
+        }
     }
 }
 
@@ -391,8 +404,10 @@ extern "C" int sfb_render_final(sfb_ctx* ctx, const void* screen_rgba8_dev, int 
                   width, height, subsample, components, static_cast<unsigned char*>(dst_dev), 1.0/double(width), 1.0/double(height)};
     dim3 block(32, 8), grid((width + 31)/32, (height + 7)/8);
     static const bool generic_only = getenv("SFB_FINAL_GENERIC") != nullptr;       // debugging knob
-    if (subsample == 2 && screen_w == width && screen_h == height && !generic_only)
-        final_half_step_kernel<<<grid, block, 0, ctx->stream>>>(P);               // the reference's default export
+    if (subsample == 2 && screen_w == width && screen_h == height && !generic_only) {
+        dim3 tall((width + 31)/32, (height + FINAL_TILE_H - 1)/FINAL_TILE_H);
+        final_half_step_kernel<<<tall, block, 0, ctx->stream>>>(P);               // the reference's default export
+    }
     else
         final_kernel<<<grid, block, 0, ctx->stream>>>(P);
     SFB_LAUNCH_CHECK(ctx);

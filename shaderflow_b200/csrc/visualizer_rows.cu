@@ -61,10 +61,29 @@ struct RowsTaps {
 };
 __constant__ RowsTaps c_rows;
 
+// Per-frame constants of visualizer.frag (functions of the uniforms only): evaluated once per frame by the launcher on
+// the host — the same float32 formulas and libm calls plan_rows sizes the window with — and passed in the kernel
+// parameter block (round 2; a 1-thread kernel launched in front of every frame did this before: ~3 us per frame)
+struct FrameConsts {
+    float zf, wobx, woby, scale;       // background zoom factor, wobble, blur radius in texels (:16-17,21)
+    float std5, mscale, vexp, pad;     // 5*iAudioSTD, 1 - 0.4*pow(|vol|, 0.5), 0.1 + 0.15*vol (:35,39,71)
+};
+static inline FrameConsts frame_consts(float iTime, float volume, float stddev, float fh) {
+    FrameConsts F;
+    F.zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*volume - 0.03f;
+    F.wobx = 0.005f*cosf(iTime*3.25135f); F.woby = 0.005f*sinf(iTime*1.153469f);
+    F.scale = (0.01f*fminf(fmaxf(powf(volume, 2.5f), 0.0f), 0.3f))*fh;     // st displacement → texels (hw*fw == fh)
+    F.std5 = 5.0f*stddev;
+    F.mscale = 1.0f - 0.4f*powf(fabsf(volume), 0.5f);
+    F.vexp = 0.1f + 0.15f*volume;
+    F.pad = 0.0f;
+    return F;
+}
+
 struct VisRowsParams {
     RenderParams R;
+    FrameConsts K;                     // frame_consts() of this frame's uniforms
     int win_h;                         // window rows staged (dynamic shared memory is sized for it)
-    int slot;                          // g_frame entry written by visualizer_frame_consts_kernel for this frame
     int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
     int screen_alpha;                  // comps == 4: store fragColor.a (iScreen pass of an unfused export) instead of 255
     const void* tmap;                  // device CUtensorMap of the background with a WW x win_h box, or NULL (bulk row copies)
@@ -83,28 +102,6 @@ SFB_DEV float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=
 SFB_DEV float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // pow(x, y) for x >= 0 and the small |y| used here (<= 0.5, which shrinks the error of lg2); pow(0, y > 0) = 0
 SFB_DEV float pow_pos(float x, float y) { return fast_ex2(y*fast_lg2(x)); }
-
-// Per-frame constants of visualizer.frag (functions of the uniforms only), evaluated once per frame by
-// visualizer_frame_consts_kernel with the same libdevice calls as the literal transliteration
-struct FrameConsts {
-    float zf, wobx, woby, scale;       // background zoom factor, wobble, blur radius in texels (:16-17,21)
-    float std5, mscale, vexp, pad;     // 5*iAudioSTD, 1 - 0.4*pow(|vol|, 0.5), 0.1 + 0.15*vol (:35,39,71)
-};
-constexpr int VR_SLOTS = 64;
-__device__ FrameConsts g_frame[VR_SLOTS];
-
-__global__ void visualizer_frame_consts_kernel(float iTime, float volume, float stddev, float fh, int slot) {
-    if (threadIdx.x != 0) return;
-    FrameConsts F;
-    F.zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*volume - 0.03f;
-    F.wobx = 0.005f*cosf(iTime*3.25135f); F.woby = 0.005f*sinf(iTime*1.153469f);
-    F.scale = (0.01f*clamp(powf(volume, 2.5f), 0.0f, 0.3f))*fh;     // st displacement → texels (hw*fw == fh)
-    F.std5 = 5.0f*stddev;
-    F.mscale = 1.0f - 0.4f*powf(fabsf(volume), 0.5f);
-    F.vexp = 0.1f + 0.15f*volume;
-    F.pad = 0.0f;
-    g_frame[slot] = F;
-}
 
 // What the back end reads of iSpectrogram when it is the usual RG32F column (spectrogram.py:272-282)
 struct SpecColumn { const float2* texels; int h, ry; };
@@ -187,7 +184,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     const int jb = blockIdx.y*(VR_GROUPS*J) + ty*J;               // first fragment row of this thread
     const DevSampler& bg = P.tex[0];
     const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
-    const FrameConsts K = g_frame[VP.slot];
+    const FrameConsts& K = VP.K;
     const float zf = K.zf, scale = K.scale;
     const vec2 wobble = mk2(K.wobx, K.woby);
 
@@ -601,7 +598,6 @@ static int build_rows_tables() {
     return SFB_OK;
 }
 
-static std::atomic<unsigned int> g_next_slot{0};
 
 template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
     static bool configured[64] = {};                      // the attribute is per device
@@ -619,10 +615,8 @@ template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP
     size_t smem = size_t(VR_TEXEL_BYTES)*WW*size_t(VP.win_h) + table;
     if (smem < epilogue) smem = epilogue;
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
-    // frame constants first (same stream): consecutive launches of the process rotate through the slots
-    VP.slot = int(g_next_slot.fetch_add(1u) % VR_SLOTS);
     const sfb_uniforms& u = VP.R.u;
-    visualizer_frame_consts_kernel<<<1, 32, 0, st>>>(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h), VP.slot);
+    VP.K = frame_consts(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h));
     visualizer_rows_kernel<S, J, WW><<<grid, block, smem, st>>>(VP);
     return cudaSuccess;
 }
@@ -645,9 +639,9 @@ static void plan_rows(const RenderParams& P, int* J_out, int* win_h_out, int* wi
     const DevSampler& bg = P.tex[0];
     const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
     const float iTime = u.iTime, vol = u.extra[0][0];
-    const float zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*vol - 0.03f;
-    const vec2 wobble = 0.005f*mk2(cosf(iTime*3.25135f), sinf(iTime*1.153469f));
-    const float scale = 0.01f*fminf(fmaxf(powf(vol, 2.5f), 0.0f), 0.3f)*fh;
+    const FrameConsts F = frame_consts(iTime, vol, 0.0f, fh);          // exactly what the kernel will get
+    const float zf = F.zf, scale = F.scale;
+    const vec2 wobble = mk2(F.wobx, F.woby);
     const vec2 t00 = vis_front(P, 0, 0, fw, fh, hw, wobble, zf).tap;
     const vec2 t10 = vis_front(P, P.Wr - 1, 0, fw, fh, hw, wobble, zf).tap;
     const vec2 t01 = vis_front(P, 0, P.Hr - 1, fw, fh, hw, wobble, zf).tap;
@@ -708,6 +702,6 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* 
     #undef SFB_ROWS_CASE
     if (e == cudaErrorInvalidValue) return SFB_OK;                 // no variant for this (S, J, WW): the tiled kernel takes it
     SFB_CUDA(e);
-    *launched = 2;                                                 // frame constants + the frame
+    *launched = 1;
     return SFB_OK;
 }

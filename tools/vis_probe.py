@@ -36,3 +36,14 @@ for _ in range(5):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); run1(); b.record(); torch.cuda.synchronize(); ts_.append(a.elapsed_time(b))
 print(f"1080p ssaa1 screen pass: best {min(ts_)*1e3:.1f} us avg {sum(ts_)/len(ts_)*1e3:.1f} us")
+final = torch.zeros((1080, 1920, 3), dtype=torch.uint8, device="cuda")
+def run2(): ctx.render_final(screen, 1920, 1080, 1920, 1080, 2, 3, final)
+for _ in range(3): run2()
+torch.cuda.synchronize()
+ts_ = []
+for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10): run2()
+    b.record(); torch.cuda.synchronize(); ts_.append(a.elapsed_time(b)/10)
+print(f"1080p final pass (subsample 2): best {min(ts_)*1e3:.1f} us")
