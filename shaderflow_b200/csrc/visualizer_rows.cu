@@ -61,14 +61,19 @@ struct RowsTaps {
 };
 __constant__ RowsTaps c_rows;
 
-// Per-frame constants of visualizer.frag (functions of the uniforms only): evaluated once per frame by the launcher on
-// the host — the same float32 formulas and libm calls plan_rows sizes the window with — and passed in the kernel
-// parameter block (round 2; a 1-thread kernel launched in front of every frame did this before: ~3 us per frame)
+// Per-frame constants of visualizer.frag (functions of the uniforms only), once per frame. Two routes, chosen per
+// kernel variant by measurement: the 96-texel-window variants (the 1080p default export: 150 us per frame) take them
+// from the kernel parameter block, filled by the launcher on the host — a 1-thread kernel in front of every frame
+// costs ~3 us, 2 % of such a frame; the 64-texel-window variants (4K 2xSSAA: 1.05 ms) read them from global memory
+// where that 1-thread kernel put them — as parameter-block operands they change ptxas' allocation of the blur loop
+// (56 / 112 B of spills instead of 16 / 32 B) and the frame takes 2 % longer, seven times what the launch costs.
 struct FrameConsts {
     float zf, wobx, woby, scale;       // background zoom factor, wobble, blur radius in texels (:16-17,21)
     float std5, mscale, vexp, pad;     // 5*iAudioSTD, 1 - 0.4*pow(|vol|, 0.5), 0.1 + 0.15*vol (:35,39,71)
 };
-static inline FrameConsts frame_consts(float iTime, float volume, float stddev, float fh) {
+constexpr int VR_SLOTS = 64;
+__device__ FrameConsts g_frame[VR_SLOTS];
+SFB_HD FrameConsts frame_consts(float iTime, float volume, float stddev, float fh) {
     FrameConsts F;
     F.zf = 0.95f + 0.01f*sinf(iTime) - 0.02f*volume - 0.03f;
     F.wobx = 0.005f*cosf(iTime*3.25135f); F.woby = 0.005f*sinf(iTime*1.153469f);
@@ -79,14 +84,18 @@ static inline FrameConsts frame_consts(float iTime, float volume, float stddev, 
     F.pad = 0.0f;
     return F;
 }
+__global__ void visualizer_frame_consts_kernel(float iTime, float volume, float stddev, float fh, int slot) {
+    if (threadIdx.x == 0) g_frame[slot] = frame_consts(iTime, volume, stddev, fh);
+}
 
 struct VisRowsParams {
     RenderParams R;
-    FrameConsts K;                     // frame_consts() of this frame's uniforms
     int win_h;                         // window rows staged (dynamic shared memory is sized for it)
     int debug;                         // SFB_ROWS_DEBUG bits (profiling only): 1 skip the taps, 2 skip the back end
     int screen_alpha;                  // comps == 4: store fragColor.a (iScreen pass of an unfused export) instead of 255
     const void* tmap;                  // device CUtensorMap of the background with a WW x win_h box, or NULL (bulk row copies)
+    int slot;                          // WW == 64: g_frame entry written by visualizer_frame_consts_kernel for this frame
+    FrameConsts K;                     // WW == 96: frame_consts() of this frame's uniforms, evaluated by the launcher
 };
 
 SFB_DEV void bulk_load_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
@@ -184,7 +193,7 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     const int jb = blockIdx.y*(VR_GROUPS*J) + ty*J;               // first fragment row of this thread
     const DevSampler& bg = P.tex[0];
     const float fw = float(bg.w), fh = float(bg.h), hw = float(bg.h)/float(bg.w);
-    const FrameConsts& K = VP.K;
+    const FrameConsts K = (WW == 64) ? g_frame[VP.slot] : VP.K;
     const float zf = K.zf, scale = K.scale;
     const vec2 wobble = mk2(K.wobx, K.woby);
 
@@ -599,6 +608,8 @@ static int build_rows_tables() {
 }
 
 
+static std::atomic<unsigned int> g_next_slot{0};
+
 template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP, cudaStream_t st) {
     static bool configured[64] = {};                      // the attribute is per device
     int device = 0;
@@ -617,6 +628,11 @@ template <int S, int J, int WW> static cudaError_t launch_rows(VisRowsParams& VP
     dim3 block(VR_COLS, VR_GROUPS), grid((VP.R.Wr + VR_COLS - 1)/VR_COLS, (VP.R.Hr + VR_GROUPS*J - 1)/(VR_GROUPS*J));
     const sfb_uniforms& u = VP.R.u;
     VP.K = frame_consts(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h));
+    VP.slot = 0;
+    if (WW == 64) {                     // same stream, in front of the frame: consecutive launches rotate through the slots
+        VP.slot = int(g_next_slot.fetch_add(1u) % VR_SLOTS);
+        visualizer_frame_consts_kernel<<<1, 32, 0, st>>>(u.iTime, u.extra[0][0], u.extra[1][0], float(VP.R.tex[0].h), VP.slot);
+    }
     visualizer_rows_kernel<S, J, WW><<<grid, block, smem, st>>>(VP);
     return cudaSuccess;
 }
@@ -702,6 +718,6 @@ int sfb_visualizer_rows_launch(const RenderParams& P, cudaStream_t stream, int* 
     #undef SFB_ROWS_CASE
     if (e == cudaErrorInvalidValue) return SFB_OK;                 // no variant for this (S, J, WW): the tiled kernel takes it
     SFB_CUDA(e);
-    *launched = 1;
+    *launched = (WW == 64) ? 2 : 1;                               // (frame constants +) the frame
     return SFB_OK;
 }
