@@ -162,6 +162,11 @@ __device__ __noinline__ void visualizer_unfitted(const RenderParams& P, int i, i
 #ifndef VR_MIN_CTAS
 #define VR_MIN_CTAS 3
 #endif
+typedef unsigned long long vr_u64;
+// two float32 lanes in one 64-bit register pair: fma.rn.f32x2 does two FMAs in one issue slot (the kernel is issue-limited)
+SFB_DEV vr_u64 pack2(float lo, float hi) { vr_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+SFB_DEV void unpack2(vr_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SFB_DEV vr_u64 fma2(vr_u64 a, vr_u64 b, vr_u64 c) { vr_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 constexpr int VR_TEXEL_BYTES = 24;                             // window bytes per texel over both planes
 constexpr int vr_max_h(int ww) { return ww == 64 ? VR_MAX_H : 32; }     // window rows a variant may stage
 
@@ -181,6 +186,12 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     float4* tblH = reinterpret_cast<float4*>(vr_smem + (sizeof(float4) + sizeof(float2))*VR_WIN_W*win_h);  // [4][VR_HG][J] hinge weights + row offset
     float4* tblM = tblH + VR_GROUPS*VR_HG*J;                                             // [4][VR_MAXQ][J] merged weights of 4 texel rows
     float* wx = reinterpret_cast<float*>(tblM + VR_GROUPS*VR_MAXQ*J);                    // [VR_NI_MAX][64] phase 2: merged horizontal weights
+    // even J: the vertical weights are laid out per PAIR of fragment rows, (w_j, w_j+1) adjacent, so that one f32x2 FMA
+    // applies a texel-row difference to two fragment rows (same region, different arrangement):
+    constexpr bool PAIRS = (J % 2) == 0;
+    float4* tblQ = tblH;                                                                 // [4][VR_HG][J/2] (h0_j, h0_j+1, h1_j, h1_j+1)
+    float2* tblW = reinterpret_cast<float2*>(tblQ + VR_GROUPS*VR_HG*(J/2));              // [4][VR_HG][J/2] (h2_j, h2_j+1)
+    __shared__ unsigned int rowoffS[VR_GROUPS][VR_HG];                                   // window row offset of each (row group, hinge group)
     __shared__ float red[2][VR_THREADS/32];
     __shared__ float cyS[VR_GROUPS][J];
     __shared__ float4 rowS[VR_GROUPS][J];                                                // (agluv.y, astuv.y, uv.y, -) per fragment row
@@ -268,7 +279,15 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             // byte offset of window row r0 in the (b, b'-b) plane, with the 2^23 exponent bits of the magic
             // floor of x folded in (modulo 2^32); the (r, g) plane uses twice this offset
             const unsigned int rowoff = (unsigned int)r0*(VR_WIN_W*8u) - (0x4B000000u << 3);
-            tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+            if constexpr (PAIRS) {
+                const int slot = (g*VR_HG + k)*(J/2) + (r >> 1), odd = r & 1;
+                reinterpret_cast<float*>(tblQ + slot)[odd] = __saturatef(t);
+                reinterpret_cast<float*>(tblQ + slot)[2 + odd] = __saturatef(t - 1.0f);
+                reinterpret_cast<float*>(tblW + slot)[odd] = __saturatef(t - 2.0f);
+                if (r == 0) rowoffS[g][k] = rowoff;
+            } else {
+                tblH[e] = make_float4(__saturatef(t), __saturatef(t - 1.0f), __saturatef(t - 2.0f), __uint_as_float(rowoff));
+            }
         }
         // merged weights of the dx = 0 taps: W[g][row][r] = sum over the 21 taps of hat(py - row), the
         // bilinear weight of texel row `row` (hat(t) = max(0, 1 - |t|)); one entry per loop trip
@@ -284,7 +303,13 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             float w = 0.0f;
             #pragma unroll 7
             for (int k = 0; k < VR_VTAPS; k++) w += fmaxf(1.0f - fabsf(fmaf(c_rows.vdy[k], scale, cy)), 0.0f);
-            reinterpret_cast<float*>(tblM + (g*VR_MAXQ + (row >> 2))*J + r)[row & 3] = w;
+            if constexpr (PAIRS) {   // texel rows (4q, 4q+1) of fragment rows (j, j+1) in one float4, rows (4q+2, 4q+3) in the next
+                const int c = row & 3;
+                float* quad = reinterpret_cast<float*>(tblM + (((g*VR_MAXQ + (row >> 2))*(J/2) + (r >> 1))*2 + (c >> 1)));
+                quad[(c & 1)*2 + (r & 1)] = w;
+            } else {
+                reinterpret_cast<float*>(tblM + (g*VR_MAXQ + (row >> 2))*J + r)[row & 3] = w;
+            }
             if (rem == 0) { mhdr[g][0] = (unsigned int)ry0*(VR_WIN_W*8u) - (0x4B000000u << 3); mhdr[g][1] = (unsigned int)nq; }
         }
         if (bad) win[4] = 1;                                       // benign race: every writer stores 1
@@ -356,6 +381,9 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
     #pragma unroll
     for (int r = 0; r < J; r++) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; }
     if (fits && !(VP.debug & 1)) {
+        vr_u64 acc2[PAIRS ? J/2 : 1][3];                           // even J: channel c of fragment rows (2jp, 2jp + 1)
+        #pragma unroll
+        for (int jp = 0; jp < (PAIRS ? J/2 : 1); jp++) { acc2[jp][0] = 0ull; acc2[jp][1] = 0ull; acc2[jp][2] = 0ull; }
         const float cx = tapx - float(x0);                         // tile-local, >= 1 by construction of x0
         const char* rgB = reinterpret_cast<const char*>(rg);
         const char* bbB = reinterpret_cast<const char*>(bb);
@@ -395,8 +423,52 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             }
         };
 
+        // the same for even J, two fragment rows per f32x2 FMA: the differences are duplicated into both lanes once per
+        // application (9 moves for J rows), the weights of a row pair are adjacent in the table (LDS.128 + LDS.64)
+        auto apply2 = [&](int k, const float (&H)[VR_ROWS][3]) {
+            base0 += H[0][0]; base1 += H[0][1]; base2 += H[0][2];
+            vr_u64 D2[VR_ROWS - 1][3];
+            #pragma unroll
+            for (int r = 0; r < VR_ROWS - 1; r++) {
+                #pragma unroll
+                for (int c = 0; c < 3; c++) { const float d = H[r + 1][c] - H[r][c]; D2[r][c] = pack2(d, d); }
+            }
+            const ulonglong2* Q = reinterpret_cast<const ulonglong2*>(tblQ + (ty*VR_HG + k)*(J/2));
+            const vr_u64* Wt = reinterpret_cast<const vr_u64*>(tblW + (ty*VR_HG + k)*(J/2));
+            #pragma unroll
+            for (int jp = 0; jp < J/2; jp++) {
+                const ulonglong2 w = Q[jp];
+                const vr_u64 w2 = Wt[jp];
+                #pragma unroll
+                for (int c = 0; c < 3; c++)
+                    acc2[jp][c] = fma2(w.x, D2[0][c], fma2(w.y, D2[1][c], fma2(w2, D2[2][c], acc2[jp][c])));
+            }
+        };
+
         // phase 1: the dx = 0 taps through the merged weights, 4 texel rows at a time
-        {
+        if constexpr (PAIRS) {
+            const ulonglong2* M = reinterpret_cast<const ulonglong2*>(tblM + ty*(VR_MAXQ*J));
+            unsigned int rowoff = mhdr[ty][0];
+            const int nq = int(mhdr[ty][1]);
+            #pragma unroll 1
+            for (int q = 0; q < nq; q++, rowoff += 4u*(VR_WIN_W*8u)) {
+                float H[VR_ROWS][3];
+                gather(0.0f, rowoff, H, true);
+                vr_u64 H2[VR_ROWS][3];
+                #pragma unroll
+                for (int r = 0; r < VR_ROWS; r++) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) H2[r][c] = pack2(H[r][c], H[r][c]);
+                }
+                #pragma unroll
+                for (int jp = 0; jp < J/2; jp++) {
+                    const ulonglong2 wa = M[(q*(J/2) + jp)*2], wb = M[(q*(J/2) + jp)*2 + 1];
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        acc2[jp][c] = fma2(wa.x, H2[0][c], fma2(wa.y, H2[1][c], fma2(wb.x, H2[2][c], fma2(wb.y, H2[3][c], acc2[jp][c]))));
+                }
+            }
+        } else {
             const float4* M = tblM + ty*(VR_MAXQ*J);
             unsigned int rowoff = mhdr[ty][0];
             const int nq = int(mhdr[ty][1]);
@@ -418,8 +490,10 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
         if (merged_x) {
             // one pass over the ni texel columns with the merged weights: per column and texel row one 8-byte and one
             // 4-byte load (r, g, b of the record; the differences are not needed) instead of 20 two-texel gathers
-            const float4 e0 = T[0];
-            const unsigned int base8 = __float_as_uint(e0.w) + (0x4B000000u << 3) + ((unsigned int)ix0 << 3);
+            float4 e0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            unsigned int rowoff0;
+            if constexpr (PAIRS) rowoff0 = rowoffS[ty][0]; else { e0 = T[0]; rowoff0 = __float_as_uint(e0.w); }
+            const unsigned int base8 = rowoff0 + (0x4B000000u << 3) + ((unsigned int)ix0 << 3);
             const char* pr = rgB + 2u*base8;
             const char* pb = bbB + base8;
             const float* wk = wx + tx;
@@ -436,10 +510,11 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
                     H[r][0] = fmaf(w, q.x, H[r][0]); H[r][1] = fmaf(w, q.y, H[r][1]); H[r][2] = fmaf(w, b, H[r][2]);
                 }
             }
-            apply(T, e0, H);
+            if constexpr (PAIRS) apply2(0, H); else apply(T, e0, H);
         } else {
-            const float4 e0 = T[0];
-            const unsigned int rowoff = __float_as_uint(e0.w);
+            float4 e0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            unsigned int rowoff;
+            if constexpr (PAIRS) rowoff = rowoffS[ty][0]; else { e0 = T[0]; rowoff = __float_as_uint(e0.w); }
             float H[VR_ROWS][3];
             gather(c_rows.hdx[0], rowoff, H, true);
             #pragma unroll 3
@@ -448,18 +523,26 @@ visualizer_rows_kernel(const __grid_constant__ VisRowsParams VP) {
             for (int r = 0; r < VR_ROWS; r++) { H[r][0] += H[r][0]; H[r][1] += H[r][1]; H[r][2] += H[r][2]; }
             #pragma unroll 2
             for (int t = 10; t < 20; t++) gather(c_rows.hdx[t], rowoff, H, false);
-            apply(T, e0, H);
+            if constexpr (PAIRS) apply2(0, H); else apply(T, e0, H);
         }
         // phase 3: the diagonal rays, two taps per vertical group
         #pragma unroll 2
         for (int p = 0; p < 20; p++) {
             const float4* Tp = T + (p + 1)*J;
-            const float4 e0 = Tp[0];
-            const unsigned int rowoff = __float_as_uint(e0.w);
+            float4 e0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            unsigned int rowoff;
+            if constexpr (PAIRS) rowoff = rowoffS[ty][p + 1]; else { e0 = Tp[0]; rowoff = __float_as_uint(e0.w); }
             float H[VR_ROWS][3];
             gather(c_rows.pdx[2*p], rowoff, H, true);
             gather(c_rows.pdx[2*p + 1], rowoff, H, false);
-            apply(Tp, e0, H);
+            if constexpr (PAIRS) apply2(p + 1, H); else apply(Tp, e0, H);
+        }
+        if constexpr (PAIRS) {
+            #pragma unroll
+            for (int jp = 0; jp < J/2; jp++) {
+                #pragma unroll
+                for (int c = 0; c < 3; c++) unpack2(acc2[jp][c], acc[2*jp][c], acc[2*jp + 1][c]);
+            }
         }
     }
 
