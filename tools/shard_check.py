@@ -49,6 +49,21 @@ for run in range(2):                                   # twice: the rings / stag
         ok = ok and good
         print(f"world {world} run {run}: sink {sum(a == b for a, b in zip(sink, want))}/{frames} frames identical, "
               f"hbm {sum(a == b for a, b in zip(hbm, want))}/{frames} -> {'OK' if good else 'MISMATCH'}", flush=True)
+
+# A scene with GPU feedback (MotionBlur averages its own last frames: temporal texture) must NOT shard: every rank calls
+# main() under torchrun, rank 0 exports alone, and the bytes are those of a plain single-process export.
+from examples.demo import MotionBlur
+MotionBlur.background = synthetic_background(320, 180)
+blur = MotionBlur(device=local)
+blur_flags = dict(width=320, height=180, ssaa=1, subsample=1, fps=60.0, time=24/60)
+under_torchrun = blur.main(output=bytes, **blur_flags)
+if rank == 0:
+    alone = blur.main(output=bytes, distributed=False, **blur_flags)
+    good = under_torchrun == alone and len(alone) == 320*180*3*24
+    ok = ok and good
+    print(f"world {world}: feedback scene (MotionBlur) exported by rank 0 alone -> {'OK' if good else 'MISMATCH'}", flush=True)
+else:
+    ok = ok and under_torchrun is None
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
 sys.exit(0 if ok else 1)
