@@ -170,6 +170,7 @@ struct ShaderBase {
     vec4 gl_FragCoord;
     vec4 fragColor;
     bool sfb_discarded;
+    float sfb_dscale;                 // fragments between this lane and its quad neighbours, inverted (jit_kernels.cuh)
     const RenderParams* sfb_params;
 
     G_DEV static float lerp64(double x0, double x1, double t) { return float(x0 + (x1 - x0)*t); }
@@ -210,7 +211,22 @@ struct ShaderBase {
         gl_FragCoord = vec4(float(i) + 0.5f, float(j) + 0.5f, 0.5f, 1.0f);
         fragColor = vec4(0.0f);
         sfb_discarded = false;
+        sfb_dscale = 1.0f;
     }
+
+    // screen-space derivatives (GLSL 3.30 §8.13.1): differences inside the 2 x 2 quad a group of four lanes shades.
+    // Undefined in non-uniform control flow, as in GLSL (lanes that are not executing contribute their own value).
+    G_DEV float sfb_quad_difference(float v, int axis_bit) const {
+        const float other = __shfl_xor_sync(__activemask(), v, axis_bit);
+        return (((threadIdx.x & axis_bit) != 0) ? (v - other) : (other - v))*sfb_dscale;
+    }
+    template <class V> G_DEV V sfb_quad_difference_of(const V& v, int axis_bit) const {
+        if constexpr (info<V>::n == 1) return V(sfb_quad_difference(float(v), axis_bit));
+        else { V r; for (int k = 0; k < info<V>::n; k++) r.v[k] = sfb_quad_difference(v.v[k], axis_bit); return r; }
+    }
+    template <class V> G_DEV auto dFdx(const V& v) const { return sfb_quad_difference_of(v, 1); }
+    template <class V> G_DEV auto dFdy(const V& v) const { return sfb_quad_difference_of(v, 2); }
+    template <class V> G_DEV auto fwidth(const V& v) const { return abs(dFdx(v)) + abs(dFdy(v)); }
     G_DEV sampler2D sfb_sampler(int slot) const { sampler2D s; s.s = &sfb_params->tex[slot]; return s; }
     // module / user uniforms: float components as floats, int / uint / bool components as their 32 bits
     template <class T> G_DEV T sfb_extra(int slot) const {

@@ -43,7 +43,7 @@ CXX_RESERVED = {
     "alignas", "alignof", "decltype", "constexpr", "noexcept", "static_assert", "thread_local", "wchar_t", "export",
     "near", "far", "min", "max",
 } - {"min", "max", "near", "far"}
-UNSUPPORTED_CALLS = {"dFdx", "dFdy", "fwidth", "textureGrad", "textureOffset", "texelFetchOffset", "textureProj",
+UNSUPPORTED_CALLS = {"textureGrad", "textureOffset", "texelFetchOffset", "textureProj",
                      "noise1", "noise2", "noise3", "noise4", "modf", "frexp", "ldexp"}
 
 
