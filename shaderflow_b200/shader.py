@@ -218,8 +218,12 @@ class ShaderProgram(ShaderModule):
             raise RuntimeError(logger.error(
                 f"ShaderProgram '{self.name}': the fragment shader could not be compiled for the CUDA backend: {error}")) from None
         self.release_runtime()
-        self.scene_id = self._runtime_scene = self.scene.cuda.program_load(image, len(translation.samplers))
-        self._runtime_key = key
+        if self.scene.cuda is None:
+            # a dry scene (no device): the text has been translated and compiled — a syntax / type check — but nothing is loaded
+            self.scene_id = N.SCENE_PROGRAM_BASE
+        else:
+            self.scene_id = self._runtime_scene = self.scene.cuda.program_load(image, len(translation.samplers))
+            self._runtime_key = key
         self.scene_info = dict(name=f"runtime:{registry.digest(self.fragment)}", extra=list(translation.extra),
                                extra_types=list(translation.extra_types), samplers=list(translation.samplers),
                                required=len(translation.samplers))

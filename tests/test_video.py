@@ -44,3 +44,41 @@ def test_headerless_frames(tmp_path):
     info = video.raw_info(path, 16, 8, 30.0, N.VIDEO_RGB24, bottom_up=True)
     assert info.frames == 3 and not info.top_down and info.frame_bytes == 16*8*3
     assert np.array_equal(np.asarray(video.FileFrames(path, info).frame(2)).reshape(8, 16, 3), clip[2])
+
+
+def test_dry_scene_checks_its_glsl_and_steps_the_video_rule(tmp_path):
+    """Without a device (`backend="dry"`) a scene still compiles its own GLSL — translator + NVRTC, so a typo is found
+    before any GPU is involved — and ShaderVideo still applies video.py:57-66's rule: one more frame is consumed whenever
+    scene.time > frames_read/fps"""
+    import ctypes.util
+    from pathlib import Path
+    if not (ctypes.util.find_library("nvrtc") or Path("/usr/local/cuda/lib64/libnvrtc.so.12").exists()):
+        pytest.skip("libnvrtc is not installed")
+    import examples.demo as demo
+    from shaderflow.video import ShaderVideo
+    clip = synthetic.video_frames(32, 18, 9)
+    synthetic.write_y4m(tmp_path/"clip.y4m", clip, fps=24, colorspace="420jpeg")
+    consumed = []
+
+    class Player(demo.ShaderScene):
+        def build(self):
+            self.video = ShaderVideo(scene=self, path=tmp_path/"clip.y4m")
+            self.shader.fragment = "void main() { fragColor = vec4(astexture(iVideo, astuv).rgb*iTau, 1.0); }"
+        def update(self):
+            consumed.append((self.time, self.video._frames))
+    scene = Player(backend="dry")
+    scene.main(width=32, height=18, fps=60.0, time=0.5)
+    assert scene.shader.scene_id >= 1000 and scene.shader.scene_info["samplers"] == ["iVideo0x0"]
+    assert (scene.video.width, scene.video.height, scene.video.fps) == (32, 18, 24.0) and len(consumed) == 30
+    read = 0
+    for time, before in consumed:                  # the scene's update runs before the video's in the same frame
+        assert before == read
+        if time > read/24.0:
+            read += 1
+    assert 9 < read <= 13                          # the clip has 9 frames: past its end the counter runs on, the last frame stays
+
+    class Typo(demo.ShaderScene):
+        def build(self):
+            self.shader.fragment = "void main() { fragColor = vec4(astuv, iTimee, 1.0); }"
+    with pytest.raises(RuntimeError, match="iTimee"):
+        Typo(backend="dry").main(width=32, height=18, time=0.1)
