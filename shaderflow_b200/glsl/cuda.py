@@ -126,6 +126,14 @@ class Emitter:
         self.lines: list[str] = []
         self.depth = 1
         self.rtype = "void"
+        # positions of out / inout parameters per user function name (any overload of that arity)
+        self.writes: dict[tuple[str, int], set[int]] = {}
+        for item in items:
+            if item[0] == "function":
+                _, _, name, params, _ = item
+                slots = self.writes.setdefault((name, len(params)), set())
+                slots.update(k for k, (direction, _, _) in enumerate(params) if direction != "in")
+        self.function_returns = {(item[2], len(item[3])): item[1] for item in items if item[0] == "function"}
 
     # -- types ----------------------------------------------------------------------------------
     def ctype(self, t) -> str:
@@ -172,6 +180,21 @@ class Emitter:
             _, name, args = e
             if name in UNSUPPORTED_CALLS:
                 raise TranslationError(f"builtin '{name}' is not supported by the CUDA backend")
+            # a swizzle handed to an out / inout parameter (`rotate(p.xz, a)`): copy in, call, copy back
+            swizzled = [k for k in self.writes.get((name, len(args)), ()) if args[k][0] == "field"
+                        and args[k][2] not in self.struct_fields and is_swizzle(args[k][2]) and len(args[k][2]) > 1]
+            if swizzled:
+                texts = [self.expr(a) for a in args]
+                before, after = [], []
+                for k in swizzled:
+                    base, idx = self.expr(args[k][1]), swizzle_indices(args[k][2])
+                    before.append(f"auto sfb_arg{k} = swz<{idx}>({base});")
+                    after.append(f"swz_set<{idx}>({base}, sfb_arg{k});")
+                    texts[k] = f"sfb_arg{k}"
+                call = f"{ident(name)}({', '.join(texts)})"
+                if self.function_returns.get((name, len(args)), "void") == "void":
+                    return "[&]() { " + " ".join(before) + f" {call}; " + " ".join(after) + " }()"
+                return "[&]() { " + " ".join(before) + f" auto sfb_result = {call}; " + " ".join(after) + " return sfb_result; }()"
             return f"{ident(name)}({', '.join(self.expr(a) for a in args)})"
         if kind == "construct":
             _, t, args = e

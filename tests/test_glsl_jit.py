@@ -60,6 +60,21 @@ def test_arrays_constants_loops_and_discard():
     assert "for (; (i < length_of(K)); (++i))" in t.source
 
 
+def test_swizzles_as_out_arguments_copy_in_and_back():
+    """`rotate(p.xz, a)` with an inout parameter: a swizzle is not an lvalue in C++, so the call copies in, calls, copies back"""
+    text = """
+        void pR(inout vec2 p, float a) { p = cos(a)*p + sin(a)*vec2(p.y, -p.x); }
+        float fold(inout vec3 p, out float side) { side = sign(p.x); p.x = abs(p.x); return length(p.xy); }
+        void main() { vec3 p = vec3(gluv, 1.0); pR(p.xz, iTime); float s; float d = fold(p.zyx, s); pR(p.xy, d); fragColor = vec4(p, s); }"""
+    t = glsl.translate(text)
+    assert "[&]() { auto sfb_arg0 = swz<0, 2>(p); pR(sfb_arg0, iTime); swz_set<0, 2>(p, sfb_arg0); }();" in t.source
+    assert "auto sfb_result = fold(sfb_arg0, s); swz_set<2, 1, 0>(p, sfb_arg0); return sfb_result; }()" in t.source
+    assert "pR(sfb_arg0, d)" in t.source                      # .xy is a swizzle too
+    if ctypes.util.find_library("nvrtc") or Path("/usr/local/cuda/lib64/libnvrtc.so.12").exists():
+        image, _ = N.jit_compile(glsl.program(t), glsl.headers())
+        assert image[:4] == b"\x7fELF"
+
+
 def test_translation_errors_are_reported():
     with pytest.raises(glsl.TranslationError, match="no main"):
         glsl.translate("float f() { return 1.0; }")
