@@ -1,7 +1,8 @@
 """CPU checks of the mathematical facts the separable visualizer kernel (csrc/visualizer_rows.cu) rests on, on the
 oracle's own arithmetic — no GPU: (1) under the export camera the blur's centre tap is separable in (column, row);
 (2) the strict-float32 tap table has the coincidences the tap grouping uses; (3) a bilinear tap equals the horizontal
-lerp followed by the hinge-weight vertical interpolation; (4) vertical weights of taps sharing dx may be merged."""
+lerp followed by the hinge-weight vertical interpolation; (4) vertical weights of taps sharing dx may be merged;
+(5) horizontal lerps of taps sharing dy add up to one weighted sum over ni = floor(2*scale) + 3 texel columns."""
 import numpy as np
 
 from oracle import glsl_np as G
@@ -92,3 +93,26 @@ def test_vertical_weights_of_taps_sharing_dx_merge():
     direct = sum(H[int(np.floor(p))]*(1 - (p - np.floor(p))) + H[int(np.floor(p)) + 1]*(p - np.floor(p)) for p in py)
     merged = sum(H[row]*hat(py - row).sum() for row in range(16))
     assert np.allclose(direct, merged, atol=1e-9)
+
+
+def test_horizontal_weights_of_taps_sharing_dy_merge():
+    """Phase 2 of the rows kernel: the 20 taps of rays 0° (weighted twice: it also stands for the 9th direction) and 180°
+    read the same texel rows, so sum_k w_k * lerp(T, px_k) = sum_i T[i] * sum_k w_k * hat(px_k - i) over the
+    ni = floor(2*scale*1.0001) + 3 texel columns starting at floor(cx - scale*1.0001) — never more, whatever the phase"""
+    rng = np.random.default_rng(2)
+    t = blur_table()
+    hat = lambda d: np.maximum(0.0, 1.0 - np.abs(d))
+    dx = np.concatenate([t[0, :, 0], t[4, :, 0]]).astype(np.float64)          # ray 0 (10 walks), ray 180
+    weight = np.concatenate([np.full(10, 2.0), np.full(10, 1.0)])
+    for scale in (0.0, 0.05, 0.53, 1.0, 2.499, 2.5, 3.24):
+        ni = int(2.0*scale*1.0001) + 3
+        for _ in range(200):
+            T = rng.integers(0, 256, (40, 3)).astype(np.float64)               # one texel row
+            cx = rng.uniform(6.0, 30.0)
+            px = cx + dx*scale
+            i, a = np.floor(px).astype(int), px - np.floor(px)
+            direct = (weight[:, None]*(T[i] + a[:, None]*(T[i + 1] - T[i]))).sum(axis=0)
+            ix0 = int(np.floor(cx - scale*1.0001))
+            wx = np.array([(weight*hat(px - (ix0 + k))).sum() for k in range(ni)])
+            assert np.allclose(direct, (wx[:, None]*T[ix0:ix0 + ni]).sum(axis=0), atol=1e-9)
+            assert abs(wx.sum() - 30.0) < 1e-9                                 # every tap's two weights are inside the ni columns
