@@ -1,6 +1,7 @@
-// The video texture over the whole frame, aspect-correct (written for this repository; compiled at run time by the
-// GLSL -> CUDA translator: there is no ahead-of-time kernel for it).
+// The video texture over the whole frame, aspect-correct. Written for this repository; there is no ahead-of-time
+// kernel for it: the GLSL -> CUDA translator compiles it when the scene compiles.
 void main() {
-    GetCamera(iCamera);
-    fragColor = vec4(stexture(iVideo, iCamera.stuv).rgb, 1.0);
+    GetCamera(view);
+    vec3 rgb = stexture(iVideo, view.stuv).rgb;
+    fragColor = vec4(rgb, 1.0);
 }
