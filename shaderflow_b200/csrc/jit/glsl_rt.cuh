@@ -336,7 +336,11 @@ G_DEV int wrap_index(int i, int n, int repeat) {
     if (repeat) { i %= n; return (i < 0) ? i + n : i; }
     return ::min(::max(i, 0), n - 1);
 }
+#ifdef SFB_HOST_SHIM            // tests/test_glsl_host.py compiles this header for the host to check the translator without a GPU
+G_DEV float half_bits_to_float(unsigned short h) { return sfb_host_half_to_float(h); }
+#else
 G_DEV float half_bits_to_float(unsigned short h) { float f; asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h)); return f; }
+#endif
 
 G_DEV vec4 texel_at(const DevSampler& s, int ix, int iy) {
     ix = wrap_index(ix, s.w, s.rx);
