@@ -425,6 +425,11 @@ class Context:
             stream = torch.cuda.current_stream(device).cuda_stream
         check(lib().sfb_ctx_create(device, c_void_p(stream), byref(self.handle)))
 
+    @property
+    def torch_device(self) -> str:
+        """Where tensors handed to this context live"""
+        return f"cuda:{self.device}"
+
     def set_stream(self, stream: int) -> None:
         check(lib().sfb_ctx_set_stream(self.handle, c_void_p(stream)))
 

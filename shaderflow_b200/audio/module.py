@@ -6,8 +6,11 @@ uploaded once and stays resident in HBM as planar float32; every per-frame quant
 frames at once by csrc/audio.cu and published frame by frame. `tell`, `get_last_n_samples` & co. keep
 their meaning (they read the clip at the current frame's position).
 
-Audio enters through `load(pcm, samplerate)` (numpy, shape (channels, samples)), a WAV file, or — when
-an ffmpeg binary exists — any file ffmpeg decodes. Soundcard capture / playback is out of scope."""
+Audio enters through `load(pcm, samplerate)` (numpy, shape (channels, samples)), a WAV / FLAC file, or — when
+an ffmpeg binary exists — any file ffmpeg decodes. A scene that only knows its audio frame by frame (a synthesiser in
+`update()`) feeds `add_data(chunk)` like the reference: the clip then GROWS in HBM (only the new samples are uploaded)
+and the per-frame tracks are recomputed by the same batch kernels over the frames seen so far, so a streamed export
+equals the batch export of the same samples. Soundcard capture / playback is out of scope."""
 from __future__ import annotations
 
 import math
@@ -83,6 +86,7 @@ class BrokenAudio:
         self.clip = np.ascontiguousarray(pcm)
         self.clip_device = None
         self._wav = None
+        self.streaming, self._stream_host, self._stream_uploaded = False, None, 0
         self._channels = int(pcm.shape[0])
         if samplerate:
             self._samplerate = samplerate
@@ -97,6 +101,9 @@ class BrokenAudio:
     def device_clip(self, device: int):
         if self.clip is None:
             raise RuntimeError("No audio loaded: set `file=` to an existing file or call load(pcm, samplerate)")
+        if self.streaming:
+            ctx = getattr(getattr(self, "scene", None), "cuda", None)
+            return self._stream_device_clip(getattr(ctx, "torch_device", f"cuda:{device}"))
         if self.clip_device is None:
             import torch
             ctx = getattr(getattr(self, "scene", None), "cuda", None)
@@ -120,9 +127,57 @@ class BrokenAudio:
             out[:, self.buffer_size - n:] = self.clip[:, self.tell - n:self.tell]
         return out
 
+    # -- streaming ---------------------------------------------------------------------------------
+    streaming: bool = False
+    """True once add_data() has been called: the clip is what was added so far and `tell` its length"""
+    _stream_host: Any = field(default=None, repr=False)
+    """(channels, capacity) float32; `clip` is the view of its first `tell` samples"""
+    _stream_uploaded: int = 0
+    """Samples of the stream that already are in `clip_device` (channels, device capacity)"""
+
     def add_data(self, data: np.ndarray) -> Optional[np.ndarray]:
-        raise NotImplementedError(
-            "Streaming add_data() is not supported by the CUDA backend; give it the whole clip with load()")
+        """audio/module.py:113-129: append (channels, length) samples; `tell` advances by length. Instead of rolling
+        a 30 s ring the samples extend the clip (amortised doubling), so `data`, `get_last_n_samples` & co. read
+        what the reference's ring would hold and the kernels index the stream by absolute sample"""
+        data = np.array(data, dtype=np.float32)
+        if data.ndim == 1:
+            data = data[None, :]
+        if not self.streaming:
+            if self.clip is not None:
+                raise RuntimeError("add_data() after load() / file=: a clip is either loaded whole or streamed")
+            self._channels = int(data.shape[0])
+            self._stream_host = np.zeros((self._channels, max(1 << 16, 2*data.shape[1])), dtype=np.float32)
+            self._stream_uploaded, self.clip_device, self._wav = 0, None, None
+            self.streaming, self.tell = True, 0
+        if data.shape[0] != self._stream_host.shape[0]:
+            raise ValueError(f"add_data(): {data.shape[0]} channels into a stream of {self._stream_host.shape[0]}")
+        length, have = int(data.shape[1]), int(self.tell)
+        if have + length > self._stream_host.shape[1]:
+            grown = np.zeros((self._stream_host.shape[0], max(2*self._stream_host.shape[1], have + length)), dtype=np.float32)
+            grown[:, :have] = self._stream_host[:, :have]
+            self._stream_host = grown
+        self._stream_host[:, have:have + length] = data
+        self.tell = have + length
+        self.clip = self._stream_host[:, :self.tell]
+        return data
+
+    def _stream_device_clip(self, device: str):
+        """The stream in HBM: (channels, capacity) planar float32, zero beyond `tell`; only samples added since the
+        last call cross PCIe. The kernels take the capacity as the plane stride and never read at or past `tell`"""
+        import torch
+        have, buf = int(self.tell), self.clip_device
+        if buf is None or buf.shape[1] < have or str(buf.device) != str(torch.device(device)):
+            grown = torch.zeros((self._stream_host.shape[0], max(1 << 20, 2*have)), dtype=torch.float32, device=device)
+            if buf is not None and str(buf.device) == str(grown.device):
+                grown[:, :self._stream_uploaded] = buf[:, :self._stream_uploaded]
+            else:
+                self._stream_uploaded = 0
+            buf = self.clip_device = grown
+        if have > self._stream_uploaded:
+            fresh = np.ascontiguousarray(self._stream_host[:, self._stream_uploaded:have])
+            buf[:, self._stream_uploaded:have] = torch.from_numpy(fresh).to(device)
+            self._stream_uploaded = have
+        return buf
 
     def get_last_n_samples(self, n: int, *, offset: int = 0) -> np.ndarray:
         """audio/module.py:137-138: the newest sample is excluded"""
@@ -241,10 +296,18 @@ class ShaderAudio(BrokenAudio, ShaderModule):
 
     @property
     def duration(self) -> float:
-        return 0.0 if self.clip is None else self.total_samples/self.samplerate
+        if self.clip is None or self.streaming:      # a stream has no length of its own: the scene's runtime decides
+            return 0.0
+        return self.total_samples/self.samplerate
+
+    stream: Any = field(default=None, repr=False)
+    """Streaming only: dict(frames, tell, dt, tell_device, dt_device) — the clock of the frames seen so far this
+    export, recorded as they happen (there is no clip to derive it from); the other audio modules read it"""
 
     def setup(self):
-        self.clock, self.scalars, self.tell = None, None, 0
+        self.clock, self.scalars, self.stream = None, None, None
+        if not self.streaming:
+            self.tell = 0                            # a stream keeps its position: the samples were fed by the scene
 
     def ffhook(self, ffmpeg) -> Optional[list]:
         """Mux the audio file into the export (audio/module.py:441-444)"""
@@ -266,16 +329,51 @@ class ShaderAudio(BrokenAudio, ShaderModule):
                                self.clock["dt_device"], scalars=scalars)
         self.scalars = scalars.cpu().numpy()      # one small D2H for the whole export
 
+    def _record_stream_frame(self) -> dict:
+        """One more frame of a streamed export: `tell` is what add_data() left, dt is the scene's (dynamics.py:197)"""
+        import torch
+        st = self.stream
+        if st is None:
+            st = self.stream = dict(frames=0, tell=np.zeros(256, np.int64), dt=np.zeros(256, np.float64))
+        k = st["frames"]
+        if k == st["tell"].shape[0]:
+            st["tell"], st["dt"] = (np.concatenate([a, np.zeros_like(a)]) for a in (st["tell"], st["dt"]))
+        st["tell"][k], st["dt"][k] = int(self.tell), float(self.scene.dt)
+        st["frames"] = k + 1
+        dev = getattr(self.scene.cuda, "torch_device", f"cuda:{self.scene.device}")
+        # the whole prefix again: 16 B per frame, and the tracks below are recomputed over it anyway
+        st["tell_device"] = torch.from_numpy(st["tell"][:k + 1].copy()).to(dev)
+        st["dt_device"] = torch.from_numpy(st["dt"][:k + 1].copy()).to(dev)
+        return st
+
+    def _update_stream(self) -> None:
+        """add_data() mode: volume / std of this frame from the batch kernel run over every frame so far (the two
+        ShaderDynamics are recurrences from frame 0; the scan is the one a whole-clip export runs, so both agree)"""
+        import torch
+        scene = self.scene
+        st = self._record_stream_frame()
+        if not scene.render_enabled:
+            return
+        frames = st["frames"]
+        scalars = torch.zeros((frames, N.SCALARS), dtype=torch.float64, device=st["tell_device"].device)
+        scene.cuda.audio_track(self.device_clip(scene.device), int(self.samplerate), st["tell_device"], st["dt_device"],
+                               scalars=scalars)
+        self._publish(scalars[frames - 1].cpu().numpy())
+
     def update(self):
         if self.clip is None or self.scene.cuda is None:
             return
+        if self.streaming:
+            return self._update_stream()
         if self.clock is None or self.clock["frames"] != self.scene.total_frames:
             self.prepare()
         k = min(self.scene.frame_index, self.clock["frames"] - 1)
         self.tell = int(self.clock["tell"][k])
         if not self.scene.render_enabled:
             return                                   # a frame another rank shades: the tracks hold every frame's state
-        row = self.scalars[k]
+        self._publish(self.scalars[k])
+
+    def _publish(self, row) -> None:
         # publish the GPU scan's state for this frame; the ShaderDynamics then only emit uniforms
         for dyn, value in ((self.volume, row[N.SCALAR_VOLUME]), (self.std, row[N.SCALAR_STD])):
             dyn.published = True

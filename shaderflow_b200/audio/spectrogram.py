@@ -200,7 +200,38 @@ class ShaderSpectrogram(BrokenSpectrogram, ShaderModule):
         self.texture = ShaderTexture(scene=self.scene, name=self.name, dtype=np.float32, repeat_y=False)
 
     def setup(self):
-        self.columns, self.offset = None, 0
+        self.columns, self.offset, self._stream_raw = None, 0, None
+
+    _stream_raw: Any = field(default=None, repr=False)
+    """Streaming only: (frames done, [capacity][bins][channels] unsmoothed columns) — STFT → filterbank of a frame
+    depends on the samples alone, so each frame is transformed once; the smoothing is a recurrence from frame 0"""
+
+    def _stream_columns(self):
+        """audio.add_data() mode: this frame's column from K1 on the new frame(s) + the dynamics scan over all so far"""
+        import torch
+        audio, scene = self.audio, self.scene
+        st = audio.stream
+        frames = st["frames"]
+        pcm = audio.device_clip(scene.device)
+        key = self.config_key()
+        done, raw, have = self._stream_raw if self._stream_raw is not None else (0, None, None)
+        if raw is None or have != key or done > frames - 1 or raw.shape[2] != pcm.shape[0]:
+            done, raw = 0, torch.zeros((256, self.spectrogram_bins, pcm.shape[0]), dtype=torch.float32, device=pcm.device)
+        if frames > raw.shape[0]:
+            grown = torch.zeros((max(2*raw.shape[0], frames),) + tuple(raw.shape[1:]), dtype=torch.float32, device=pcm.device)
+            grown[:done] = raw[:done]
+            raw = grown
+        if frames > done:
+            fresh, _ = self.track(scene.cuda, pcm, st["tell_device"][done:frames].contiguous(), apply_volume=self.apply_volume)
+            raw[done:frames] = fresh
+        self._stream_raw = (frames, raw, key)
+        if not scene.render_enabled and self.length_samples == 1:
+            return None
+        columns = raw[:frames].clone()
+        d = self.dynamics
+        scene.cuda.audio_track(pcm, int(audio.samplerate), st["tell_device"], st["dt_device"],
+                               spec=columns, bins=self.spectrogram_bins, dynamics=(d.frequency, d.zeta, d.response, d.precision))
+        return columns
 
     def prepare(self) -> None:
         audio, scene = self.audio, self.scene
@@ -222,11 +253,19 @@ class ShaderSpectrogram(BrokenSpectrogram, ShaderModule):
         self.offset = (self.offset + 1) % self.length_samples
         if self.audio.clip is None or self.scene.cuda is None:
             return
-        if self.columns is None or getattr(self, "_prepared_for", None) != (self.config_key(), self.scene.total_frames):
-            self.prepare()
-        if not self.scene.render_enabled and self.length_samples == 1:
-            return                                   # a frame another rank shades (a scrolling texture still needs its column)
-        k = min(self.scene.frame_index, self.columns.shape[0] - 1)
+        if getattr(self.audio, "streaming", False):
+            if getattr(self.audio, "stream", None) is None:
+                return                               # the audio module has not seen this frame (not a ShaderAudio)
+            columns = self._stream_columns()
+            if columns is None:
+                return
+            self.columns, k = columns, columns.shape[0] - 1
+        else:
+            if self.columns is None or getattr(self, "_prepared_for", None) != (self.config_key(), self.scene.total_frames):
+                self.prepare()
+            if not self.scene.render_enabled and self.length_samples == 1:
+                return                               # a frame another rank shades (a scrolling texture still needs its column)
+            k = min(self.scene.frame_index, self.columns.shape[0] - 1)
         row = self.columns[k]
         if self.length_samples == 1:
             self.texture.bind(self.columns, row.data_ptr())          # the whole texture IS this row

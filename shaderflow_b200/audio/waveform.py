@@ -79,8 +79,28 @@ class ShaderWaveform(ShaderModule):
                                wave_reducer=getattr(self.reducer, "kind", 0))
         self.rows = rows
 
+    def _stream_row(self):
+        """audio.add_data() mode: the reducer row of this frame alone (it depends on the samples, not on other frames)"""
+        import torch
+        audio, scene = self.audio, self.scene
+        st = audio.stream
+        pcm = audio.device_clip(scene.device)
+        last = st["frames"] - 1
+        row = torch.zeros((1, self._points, audio.channels), dtype=torch.float32, device=pcm.device)
+        scene.cuda.audio_track(pcm, int(audio.samplerate), st["tell_device"][last:].contiguous(), st["dt_device"][last:].contiguous(),
+                               wave=row, wave_points=self._points, wave_chunk=self.chunk_size,
+                               wave_reducer=getattr(self.reducer, "kind", 0))
+        return row
+
     def update(self):
         if self.audio.clip is None or self.scene.cuda is None:
+            return
+        if getattr(self.audio, "streaming", False):
+            if self.texture.components != self.audio.channels:
+                self.texture.components = self.audio.channels
+            if self.scene.render_enabled and getattr(self.audio, "stream", None) is not None:
+                self.rows = self._stream_row()
+                self.texture.bind(self.rows, self.rows.data_ptr())
             return
         if self.rows is None or self.rows.shape[0] != self.scene.total_frames or self.rows.shape[1] != self._points:
             self.prepare()

@@ -1,0 +1,47 @@
+"""Streaming `add_data()` on the device (audio/module.py:113-129): a scene that feeds its audio from `update()`, one
+chunk per frame, exports the bytes of the scene that was given the same samples as one clip. (Host logic without a
+GPU: tests/test_streaming.py.)"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def streamed(cls, clip: np.ndarray, tell: np.ndarray):
+    class Streamed(cls):
+        fed = 0
+
+        def update(self):
+            upto = int(tell[min(self.frame_index, len(tell) - 1)])
+            self.audio.add_data(clip[:, self.fed:upto])
+            self.fed = upto
+    return Streamed
+
+
+@pytest.mark.parametrize("fps,seconds_of_audio,seconds", [(60.0, 0.5, 0.4), (24.0, 0.3, 0.5)])
+def test_streamed_export_equals_the_whole_clip_export(fps, seconds_of_audio, seconds):
+    from shaderflow_b200 import _native as N, synthetic
+    from examples.demo import Visualizer, synthetic_background
+    clip = synthetic.noise(seconds_of_audio)
+    frames = round(seconds*fps)
+    _, _, tell = N.frame_clock(frames, fps, 1.0, 44100, 2, clip.shape[1])
+    Visualizer.background = synthetic_background(240, 135)
+    try:
+        flags = dict(width=320, height=180, ssaa=2, subsample=2, fps=fps, time=seconds, output=bytes)
+        whole = Visualizer(device=0); whole.initialize()
+        whole.audio.load(clip, 44100)
+        a = whole.main(**flags)
+        fed = streamed(Visualizer, clip, tell)(device=0); fed.initialize()
+        b = fed.main(**flags)
+    finally:
+        Visualizer.background = None
+    assert fed.audio.streaming and fed.audio.tell == int(tell[-1]) and fed.audio.stream["frames"] == frames
+    assert np.array_equal(fed.audio.stream["tell"][:frames], tell)
+    # the smoothed spectrogram columns of every frame, as the last frame's scan left them, are the batch track's
+    assert torch.equal(fed.spectrogram.columns, whole.spectrogram.columns[:frames])
+    assert torch.equal(fed.waveform.rows[0], whole.waveform.rows[frames - 1])
+    assert len(a) == len(b) == 320*180*3*frames
+    assert a == b
+    # only the new samples crossed PCIe, into a buffer that outgrows the stream
+    assert fed.audio._stream_uploaded == fed.audio.tell and fed.audio.clip_device.shape[1] >= fed.audio.tell
