@@ -1263,6 +1263,10 @@ class Machine:
             fn = self.resolve(name, args)
             return self.call_user(fn, args, mask, arg_nodes)
         args = [self.eval(a, mask) for a in arg_nodes]
+        if name in ("modf", "frexp"):                      # the two builtins with an out parameter (§8.3)
+            result, second = self.builtin(name, args[:1])
+            self.assign(arg_nodes[1], second, mask)
+            return result
         return self.builtin(name, args)
 
     def resolve(self, name, args):
@@ -1485,6 +1489,35 @@ class Machine:
     def b_texture(self, sampler, uv, bias=None):
         a, _, _ = self.fl(uv)
         return V("vec4", sampler.a.sample(a).astype(F32))
+
+    def b_textureOffset(self, sampler, uv, offset, bias=None):
+        a, _, _ = self.fl(uv)
+        o = offset.a.astype(np.int64)
+        return V("vec4", sampler.a.sample(a, offset=(o[:, 0], o[:, 1])).astype(F32))
+
+    def b_textureGrad(self, sampler, uv, dpdx, dpdy):      # one level: the gradients select nothing
+        return self.b_texture(sampler, uv)
+
+    def b_textureProj(self, sampler, p, bias=None):
+        a, _, n = self.fl(p)
+        return V("vec4", sampler.a.sample((a[:, :2]/a[:, n - 1:n]).astype(F32)).astype(F32))
+
+    def b_texelFetchOffset(self, sampler, p, lod, offset):
+        return self.b_texelFetch(sampler, V(p.t, (p.a.astype(np.int64) + offset.a.astype(np.int64)).astype(I32)), lod)
+
+    def b_modf(self, x):
+        a, t, _ = self.fl(x)
+        whole = np.trunc(a).astype(F32)
+        return V(t, (a - whole).astype(F32)), V(t, whole)
+
+    def b_frexp(self, x):
+        a, t, n = self.fl(x)
+        m, e = np.frexp(a)
+        return V(t, m.astype(F32)), V(make_type("int", n), e.astype(I32))
+
+    def b_ldexp(self, x, e):
+        a, t, _ = self.fl(x)
+        return V(t, np.ldexp(a, e.a.astype(np.int64)).astype(F32))
 
     def b_textureSize(self, sampler, lod):
         w, h = sampler.a.size

@@ -168,18 +168,20 @@ class Texture:
             t = np.concatenate([t] + pad, axis=-1)
         return t
 
-    def sample(self, uv):
-        """texture(sampler, uv) → (..., 4) float32"""
+    def sample(self, uv, offset=(0, 0)):
+        """texture(sampler, uv) → (..., 4) float32; `offset` (textureOffset, GL 3.3 §3.8.7) is a whole number of
+        texels added to the texel coordinates before the wrap mode applies"""
         uv = np.asarray(uv, F)
         W, H = self.size
+        ox, oy = (np.asarray(o, np.int64) for o in offset)
         u = (uv[..., 0]*F(W)).astype(F)
         v = (uv[..., 1]*F(H)).astype(F)
         if not self.linear:
-            return self.texels(np.floor(u).astype(np.int64), np.floor(v).astype(np.int64))
+            return self.texels(np.floor(u).astype(np.int64) + ox, np.floor(v).astype(np.int64) + oy)
         ub, vb = (u - F(0.5)).astype(F), (v - F(0.5)).astype(F)
         fx, fy = np.floor(ub), np.floor(vb)
         a, b = (ub - fx).astype(F)[..., None], (vb - fy).astype(F)[..., None]
-        i0, j0 = fx.astype(np.int64), fy.astype(np.int64)
+        i0, j0 = fx.astype(np.int64) + ox, fy.astype(np.int64) + oy
         t00, t10 = self.texels(i0, j0), self.texels(i0 + 1, j0)
         t01, t11 = self.texels(i0, j0 + 1), self.texels(i0 + 1, j0 + 1)
         top = (t00*(F(1) - a) + t10*a).astype(F)

@@ -256,6 +256,16 @@ G_F1(floor, ::floorf(x)) G_F1(ceil, ::ceilf(x)) G_F1(trunc, ::truncf(x)) G_F1(ro
 G_F1(fract, x - ::floorf(x))
 G_F1(isnan, bool(x != x)) G_F1(isinf, bool(::fabsf(x) == __int_as_float(0x7f800000)))
 G_F2(pow, ::powf(x, y))
+// modf / frexp / ldexp (GLSL 3.30 §8.3, 4.00 §8.3): the second result leaves through an out parameter
+G_DEV float modf(float x, float& whole) { whole = ::truncf(x); return x - whole; }
+template <int N> G_DEV vec<float, N> modf(const vec<float, N>& x, vec<float, N>& whole) {
+    vec<float, N> r; for (int i = 0; i < N; i++) r.v[i] = modf(x.v[i], whole.v[i]); return r; }
+G_DEV float frexp(float x, int& exponent) { return ::frexpf(x, &exponent); }
+template <int N> G_DEV vec<float, N> frexp(const vec<float, N>& x, vec<int, N>& exponent) {
+    vec<float, N> r; for (int i = 0; i < N; i++) r.v[i] = frexp(x.v[i], exponent.v[i]); return r; }
+G_DEV float ldexp(float x, int exponent) { return ::ldexpf(x, exponent); }
+template <int N> G_DEV vec<float, N> ldexp(const vec<float, N>& x, const vec<int, N>& exponent) {
+    vec<float, N> r; for (int i = 0; i < N; i++) r.v[i] = ldexp(x.v[i], exponent.v[i]); return r; }
 G_F2(mod, x - y*::floorf(x/y))
 G_F2(step, (y < x) ? 0.0f : 1.0f)
 G_F3(smoothstep_, (::fminf(::fmaxf((z - x)/(y - x), 0.0f), 1.0f)))
@@ -379,5 +389,23 @@ template <class S> G_DEV vec4 texelFetch(sampler2D t, ivec2 p, S) {
     const DevSampler& s = *t.s;
     return texel_at(s, ::min(::max(p.x, 0), s.w - 1), ::min(::max(p.y, 0), s.h - 1));
 }
+// the offset / projective / explicit-gradient forms (GLSL 3.30 §8.7). Textures here have one level, so a gradient only
+// ever selects that level; an offset is a whole number of texels added to the texel coordinates before wrapping
+G_DEV vec4 textureOffset(sampler2D t, vec2 uv, ivec2 o) {
+    const DevSampler& s = *t.s;
+    const float u = uv.x*float(s.w), v = uv.y*float(s.h);
+    if (s.filter == SFB_FILTER_NEAREST) return texel_at(s, int(::floorf(u)) + o.x, int(::floorf(v)) + o.y);
+    const float ub = u - 0.5f, vb = v - 0.5f, fx = ::floorf(ub), fy = ::floorf(vb), a = ub - fx, b = vb - fy;
+    const int i0 = int(fx) + o.x, j0 = int(fy) + o.y;
+    const vec4 t00 = texel_at(s, i0, j0), t10 = texel_at(s, i0 + 1, j0), t01 = texel_at(s, i0, j0 + 1), t11 = texel_at(s, i0 + 1, j0 + 1);
+    const vec4 top = t00*(1.0f - a) + t10*a, bot = t01*(1.0f - a) + t11*a;
+    return top*(1.0f - b) + bot*b;
+}
+template <class S> G_DEV vec4 textureOffset(sampler2D t, vec2 uv, ivec2 o, S) { return textureOffset(t, uv, o); }
+template <class S> G_DEV vec4 texelFetchOffset(sampler2D t, ivec2 p, S lod, ivec2 o) { return texelFetch(t, ivec2(p.x + o.x, p.y + o.y), lod); }
+G_DEV vec4 textureGrad(sampler2D t, vec2 uv, vec2, vec2) { return texture(t, uv); }
+G_DEV vec4 textureProj(sampler2D t, vec3 p) { return texture(t, vec2(p.x/p.z, p.y/p.z)); }
+G_DEV vec4 textureProj(sampler2D t, vec4 p) { return texture(t, vec2(p.x/p.w, p.y/p.w)); }
+template <class P, class S> G_DEV vec4 textureProj(sampler2D t, const P& p, S) { return textureProj(t, p); }
 
 }  // namespace g

@@ -43,8 +43,7 @@ CXX_RESERVED = {
     "alignas", "alignof", "decltype", "constexpr", "noexcept", "static_assert", "thread_local", "wchar_t", "export",
     "near", "far", "min", "max",
 } - {"min", "max", "near", "far"}
-UNSUPPORTED_CALLS = {"textureGrad", "textureOffset", "texelFetchOffset", "textureProj",
-                     "noise1", "noise2", "noise3", "noise4", "modf", "frexp", "ldexp"}
+UNSUPPORTED_CALLS = {"noise1", "noise2", "noise3", "noise4"}      # deprecated since GLSL 1.30; drivers return 0
 
 
 class TranslationError(RuntimeError):
@@ -134,6 +133,10 @@ class Emitter:
                 slots = self.writes.setdefault((name, len(params)), set())
                 slots.update(k for k, (direction, _, _) in enumerate(params) if direction != "in")
         self.function_returns = {(item[2], len(item[3])): item[1] for item in items if item[0] == "function"}
+        for builtin in ("modf", "frexp"):                  # the two builtins with an out parameter (GLSL 3.30 / 4.00 §8.3)
+            if (builtin, 2) not in self.function_returns:
+                self.writes[(builtin, 2)] = {1}
+                self.function_returns[(builtin, 2)] = "genType"
 
     # -- types ----------------------------------------------------------------------------------
     def ctype(self, t) -> str:

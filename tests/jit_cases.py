@@ -17,6 +17,9 @@ from oracle import glsl_np as G
 
 SHADERS = Path(__file__).parent/"shaders"
 CORPUS = ("plasma", "sdf", "bits", "textured", "idioms")
+LATE = ("offsets",)
+"""Corpus shaders added after the round's GPU budget was spent: held to the evaluator on the host (test_glsl_host.py) and
+compiled by NVRTC (test_glsl_jit.py) like the others; their device run is in tests/test_gpu_zstream.py"""
 W, H = 64, 36
 VARYINGS = ("stxy", "glxy", "stuv", "astuv", "gluv", "agluv")
 # what shader.py:190-239 declares in front of every fragment (the names the corpus reads)

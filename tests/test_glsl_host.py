@@ -84,7 +84,7 @@ def run_on_host(tmp_path, fragment: str, header: str, uniforms: G.Uniforms, extr
     return out[..., :4], out[..., 4] > 0.5
 
 
-@pytest.mark.parametrize("name", J.CORPUS)
+@pytest.mark.parametrize("name", J.CORPUS + J.LATE)
 def test_emitted_code_equals_the_evaluated_text_on_the_host(tmp_path, name):
     want, gone = J.evaluate(name)
     got, discarded = run_on_host(tmp_path, (J.SHADERS/f"{name}.frag").read_text(), J.HEADER, J.uniforms(), J.USER_UNIFORMS,

@@ -78,8 +78,11 @@ def test_swizzles_as_out_arguments_copy_in_and_back():
 def test_translation_errors_are_reported():
     with pytest.raises(glsl.TranslationError, match="no main"):
         glsl.translate("float f() { return 1.0; }")
-    with pytest.raises(glsl.TranslationError, match="textureGrad"):
-        glsl.translate("uniform sampler2D t; void main() { fragColor = textureGrad(t, astuv, vec2(0), vec2(0)); }")
+    with pytest.raises(glsl.TranslationError, match="noise3"):
+        glsl.translate("void main() { fragColor = vec4(noise3(astuv.x), 1.0); }")
+    assert "textureGrad(t, astuv" in glsl.translate("uniform sampler2D t; void main() { fragColor = textureGrad(t, astuv, vec2(0), vec2(0)); }").source
+    # modf / frexp write through their second argument: a swizzle there is copied in and back like a user function's
+    assert "swz_set<2, 3>(v, sfb_arg1)" in glsl.translate("void main() { vec4 v = vec4(0.0); fragColor.xy = modf(gluv, v.zw); fragColor.zw = v.zw; }").source
     with pytest.raises(glsl.TranslationError, match="expected"):
         glsl.translate("void main() { fragColor = vec4(1.0) }")
     many = "".join(f"uniform float u{i};" for i in range(17))
@@ -95,7 +98,7 @@ def test_float_literals_carry_the_float32_value():
 
 
 @needs_nvrtc
-@pytest.mark.parametrize("name", J.CORPUS + ("stdlib",))
+@pytest.mark.parametrize("name", J.CORPUS + J.LATE + ("stdlib",))
 def test_corpus_compiles_to_sass(name):
     header = J.STDLIB_HEADER if name == "stdlib" else J.HEADER
     image, translation, log = glsl.build((J.SHADERS/f"{name}.frag").read_text(), header)

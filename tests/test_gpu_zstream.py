@@ -1,6 +1,10 @@
-"""Streaming `add_data()` on the device (audio/module.py:113-129): a scene that feeds its audio from `update()`, one
+"""Device runs of what was written after the round's GPU budget was spent (the file sorts last on purpose: everything
+in front of it has run on a B200 before).
+
+Streaming `add_data()` on the device (audio/module.py:113-129): a scene that feeds its audio from `update()`, one
 chunk per frame, exports the bytes of the scene that was given the same samples as one clip. (Host logic without a
-GPU: tests/test_streaming.py.)"""
+GPU: tests/test_streaming.py.) The late corpus shaders of the run-time compiled path (tests/jit_cases.LATE): compiled
+program against the evaluated text, as tests/test_gpu_jit.py does for the rest of the corpus."""
 import numpy as np
 import pytest
 import torch
@@ -45,3 +49,25 @@ def test_streamed_export_equals_the_whole_clip_export(fps, seconds_of_audio, sec
     assert a == b
     # only the new samples crossed PCIe, into a buffer that outgrows the stream
     assert fed.audio._stream_uploaded == fed.audio.tell and fed.audio.clip_device.shape[1] >= fed.audio.tell
+
+
+@pytest.mark.parametrize("name", __import__("tests.jit_cases", fromlist=["LATE"]).LATE)
+def test_late_corpus_shader_equals_the_evaluated_text(name):
+    """textureOffset / texelFetchOffset / textureProj / textureGrad, modf / frexp / ldexp (tests/shaders/offsets.frag)"""
+    from oracle import glsl_np as G
+    from shaderflow_b200 import _native as N
+    from tests import jit_cases as J
+    from tests.test_gpu_jit import load, screen
+    ctx = N.Context(0)
+    try:
+        scene, info = load(ctx, name, J.HEADER)
+        want, gone = J.evaluate(name)
+        rgba, got, _ = screen(ctx, scene, info, J.uniforms(extra=dict(J.USER_UNIFORMS)), J.corpus_textures(), J.W, J.H)
+        err = np.abs(got - want)[~gone]
+        assert err.max() <= 1e-3, (name, err.max())
+        assert np.median(err) <= 1e-6 and (err <= 1e-5).mean() >= 0.99, (name, np.median(err), (err <= 1e-5).mean())
+        d = np.abs(rgba[~gone].astype(int) - G.to_unorm8(want)[~gone].astype(int))
+        assert d.max() <= 1 and (d == 0).mean() >= 0.99
+        ctx.program_unload(scene)
+    finally:
+        ctx.destroy()
