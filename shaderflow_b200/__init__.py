@@ -78,7 +78,7 @@ os.environ.setdefault("OMP_NUM_THREADS", "1")
 _SUBMODULES = (
     "variable", "message", "resolution", "scheduler", "module", "dynamics", "keyboard", "frametimer",
     "camera", "texture", "shader", "exporting", "scene", "registry", "distributed",
-    "audio", "audio.module", "audio.spectrogram", "audio.waveform", "piano", "piano.notes",
+    "audio", "audio.module", "audio.spectrogram", "audio.waveform", "piano", "piano.notes", "piano.module", "video",
 )
 
 

@@ -8,7 +8,9 @@ the rest (`sfb_video_frame`: vertical flip, planar YUV → RGB, padding, straigh
     .rgb / .raw / .rgba       headerless rgb24 / rgba frames (what this backend's own raw exports are; give width,
                               height and fps; `bottom_up=True` for an export of this backend, which is bottom row first)
     anything else             through an `ffmpeg` child (`-f rawvideo -pix_fmt rgb24`), like the reference, when the
-                              binary exists
+                              binary exists; otherwise through the libavcodec inside OpenCV (`cv2.VideoCapture`, when
+                              the package is installed): compressed files (mp4, mkv, avi, webm …) decode on the host
+                              to rgb24 and take the same upload path
 
 Frames travel file → pinned staging (two buffers) → H2D → kernel; a frame another rank shades (sharded exports) is
 skipped without being read. When the file ends the last frame stays (the reference's iterator would raise)."""
@@ -118,11 +120,49 @@ class PipeFrames:
         return self.last
 
 
+class CodecFrames:
+    """Sequential rgb24 frames of a compressed file through OpenCV's bundled FFmpeg — the same libavcodec / libswscale
+    the reference's ffmpeg child runs, in process. Used when there is no `ffmpeg` binary to pipe from"""
+    def __init__(self, path, info: VideoInfo):
+        import cv2
+        self.info, self.position, self.last, self.cv2 = info, 0, None, cv2
+        self.capture = cv2.VideoCapture(str(path))
+        if not self.capture.isOpened():
+            raise RuntimeError(f"OpenCV cannot decode '{path}'")
+
+    def __len__(self) -> int:
+        return 1 << 62
+
+    def frame(self, index: int) -> Optional[np.ndarray]:
+        while self.position <= index:
+            ok, bgr = self.capture.read()
+            if not ok:
+                return self.last                             # the stream ended: the last frame stays
+            self.last, self.position = self.cv2.cvtColor(bgr, self.cv2.COLOR_BGR2RGB).reshape(-1), self.position + 1
+        return self.last
+
+    @staticmethod
+    def available() -> bool:
+        import importlib.util
+        return importlib.util.find_spec("cv2") is not None
+
+    @staticmethod
+    def probe(path) -> tuple[int, int, float]:
+        import cv2
+        capture = cv2.VideoCapture(str(path))
+        if not capture.isOpened():
+            raise RuntimeError(f"OpenCV cannot open '{path}'")
+        width, height = int(capture.get(cv2.CAP_PROP_FRAME_WIDTH)), int(capture.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        fps = float(capture.get(cv2.CAP_PROP_FPS)) or 25.0
+        capture.release()
+        return width, height, fps
+
+
 def probe(path) -> tuple[int, int, float]:
     """(width, height, fps) through ffprobe (ffmpeg.py:1104-1113,1175-1190)"""
     ffprobe = shutil.which("ffprobe")
     if not ffprobe:
-        raise RuntimeError(f"Reading '{path}' needs ffmpeg / ffprobe on PATH; uncompressed .y4m / .rgb files are read natively")
+        raise RuntimeError(f"Reading '{path}' needs ffmpeg / ffprobe on PATH or the opencv package; uncompressed .y4m / .rgb files are read natively")
     out = subprocess.run([ffprobe, "-v", "error", "-select_streams", "v:0", "-show_entries", "stream=width,height,r_frame_rate",
                           "-of", "csv=p=0", str(path)], capture_output=True, text=True, check=True).stdout.strip().split(",")
     num, den = out[2].split("/")
@@ -160,10 +200,16 @@ class ShaderVideo(ShaderModule):
             fmt = N.VIDEO_RGBA32 if (suffix == ".rgba" or self.pixel_format == "rgba") else N.VIDEO_RGB24
             self.info = raw_info(path, self.width, self.height, self.fps, fmt, self.bottom_up)
             self._reader = FileFrames(path, self.info)
-        else:
+        elif shutil.which("ffmpeg") and shutil.which("ffprobe"):
             width, height, fps = probe(path)
             self.info = VideoInfo(width, height, fps, N.VIDEO_RGB24, width*height*3)
             self._reader = PipeFrames(path, self.info)
+        elif CodecFrames.available():
+            width, height, fps = CodecFrames.probe(path)
+            self.info = VideoInfo(width, height, fps, N.VIDEO_RGB24, width*height*3)
+            self._reader = CodecFrames(path, self.info)
+        else:
+            probe(path)                                       # raises: names what is missing
         self.width, self.height = self.info.width, self.info.height
         self.fps = self.fps or self.info.fps
         # Note: you can set .temporal (video.py:46)
@@ -172,8 +218,8 @@ class ShaderVideo(ShaderModule):
 
     def setup(self):
         self._frames = 0
-        if isinstance(self._reader, PipeFrames) and self._reader.position:
-            self._reader = PipeFrames(self.path, self.info)
+        if isinstance(self._reader, (PipeFrames, CodecFrames)) and self._reader.position:
+            self._reader = type(self._reader)(self.path, self.info)     # sequential decoders start over
 
     def update(self) -> None:
         # video.py:57-66 — only write a new frame when due; at most one per scene frame

@@ -71,3 +71,39 @@ def test_late_corpus_shader_equals_the_evaluated_text(name):
         ctx.program_unload(scene)
     finally:
         ctx.destroy()
+
+
+def test_video_scene_from_a_compressed_file_shows_the_decoded_frames(tmp_path):
+    """ShaderVideo over a lossless FFV1 stream decoded by OpenCV's libavcodec (no ffmpeg binary on the box): frame k of
+    the export shows clip frame k-1, flipped into GL's row order by sfb_video_frame, byte for byte"""
+    import shutil
+    cv2 = pytest.importorskip("cv2")
+    if shutil.which("ffmpeg") and shutil.which("ffprobe"):
+        pytest.skip("an ffmpeg binary takes precedence over the OpenCV decoder")
+    from examples.demo import ShaderScene
+    from shaderflow.video import ShaderVideo
+    from shaderflow_b200 import synthetic, video
+    W, H, n = 96, 54, 8
+    clip = synthetic.video_frames(W, H, n)
+    writer = cv2.VideoWriter(str(tmp_path/"clip.mkv"), cv2.VideoWriter_fourcc(*"FFV1"), 30.0, (W, H))
+    if not writer.isOpened():
+        pytest.skip("this OpenCV build cannot encode FFV1")
+    for frame in clip:
+        writer.write(np.ascontiguousarray(frame[..., ::-1]))
+    writer.release()
+
+    class Player(ShaderScene):
+        def build(self):
+            self.video = ShaderVideo(scene=self, path=tmp_path/"clip.mkv")
+            self.video.texture.filter = "nearest"
+            self.shader.fragment = "void main() { fragColor = vec4(astexture(iVideo, astuv).rgb, 1.0); }"
+    scene = Player()
+    shown = {}
+
+    def grab(index, pointer):
+        scene.cuda.sync(); shown[index] = scene.frame_tensor.cpu().numpy().copy()
+    scene.main(width=W, height=H, ssaa=1, subsample=1, fps=30.0, time=6/30, on_frame=grab)
+    assert (scene.video.width, scene.video.height, scene.video.fps) == (W, H, 30.0)
+    assert isinstance(scene.video._reader, video.CodecFrames)
+    for k in (1, 3, 5):                                   # same fps: frame k shows clip frame k-1 (strict > at t = 0)
+        assert np.array_equal(shown[k], np.flipud(clip[k - 1])), k

@@ -82,3 +82,52 @@ def test_dry_scene_checks_its_glsl_and_steps_the_video_rule(tmp_path):
             self.shader.fragment = "void main() { fragColor = vec4(astuv, iTimee, 1.0); }"
     with pytest.raises(RuntimeError, match="iTimee"):
         Typo(backend="dry").main(width=32, height=18, time=0.1)
+
+
+def write_with_opencv(path, clip: np.ndarray, fps: float, fourcc: str) -> None:
+    cv2 = pytest.importorskip("cv2")
+    writer = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*fourcc), fps, (clip.shape[2], clip.shape[1]))
+    if not writer.isOpened():
+        pytest.skip(f"this OpenCV build cannot encode {fourcc}")
+    for frame in clip:
+        writer.write(np.ascontiguousarray(frame[..., ::-1]))           # OpenCV's frames are BGR
+    writer.release()
+
+
+def test_compressed_files_decode_through_opencv_when_there_is_no_ffmpeg(tmp_path, monkeypatch):
+    """No ffmpeg binary (this image): a compressed file goes through the libavcodec inside OpenCV. A lossless codec
+    returns the encoder's input exactly, frame by frame; a lossy one (MPEG-4) stays close; the end of the stream keeps
+    the last frame; a dry scene steps the same update rule over it and a new export starts the decoder over"""
+    import shutil
+    monkeypatch.setattr(shutil, "which", lambda name, *a, **k: None)
+    clip = synthetic.video_frames(64, 36, 7)
+    write_with_opencv(tmp_path/"clip.mkv", clip, 24.0, "FFV1")
+    assert video.CodecFrames.probe(tmp_path/"clip.mkv") == (64, 36, 24.0)
+    info = video.VideoInfo(64, 36, 24.0, N.VIDEO_RGB24, 64*36*3)
+    frames = video.CodecFrames(tmp_path/"clip.mkv", info)
+    for k in (0, 1, 4, 6):                                             # sequential access, skipping allowed
+        got = frames.frame(k)
+        assert got.dtype == np.uint8 and got.shape == (64*36*3,) and np.array_equal(got.reshape(36, 64, 3), clip[k])
+    assert np.array_equal(frames.frame(9).reshape(36, 64, 3), clip[6]) and frames.position == 7
+    write_with_opencv(tmp_path/"clip.mp4", clip, 30.0, "mp4v")
+    lossy = video.CodecFrames(tmp_path/"clip.mp4", info)
+    error = np.abs(lossy.frame(3).reshape(36, 64, 3).astype(int) - clip[3].astype(int))
+    assert error.mean() < 12 and video.CodecFrames.probe(tmp_path/"clip.mp4")[2] == 30.0
+    with pytest.raises(RuntimeError, match="cannot"):
+        video.CodecFrames(tmp_path/"missing.mp4", info)
+
+    import examples.demo as demo
+    from shaderflow.video import ShaderVideo
+
+    class Player(demo.ShaderScene):
+        def build(self):
+            self.video = ShaderVideo(scene=self, path=tmp_path/"clip.mkv")
+            self.shader.fragment = demo.shaders/"video.frag"
+    scene = Player(backend="dry"); scene.initialize()
+    assert isinstance(scene.video._reader, video.CodecFrames) and scene.video.info.format == N.VIDEO_RGB24
+    assert (scene.video.width, scene.video.height, scene.video.fps) == (64, 36, 24.0)
+    scene.main(width=64, height=36, fps=60.0, time=0.25)
+    assert scene.video._frames == 6                                   # time 14/60 > 5/24
+    scene.video._reader.frame(2)
+    scene.main(width=64, height=36, fps=60.0, time=0.1)
+    assert scene.video._reader.position == 0 and scene.video._frames == 3
