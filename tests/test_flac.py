@@ -116,3 +116,65 @@ def test_flac_files_load_like_wav_files(tmp_path):
     with pytest.raises(ValueError, match="MD5"):
         reader.read_flac(tmp_path/"wrong.flac")
     assert reader.read_flac(tmp_path/"wrong.flac", verify=False)[0].shape == (2, 9000)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pinned to FFmpeg: streams written by libavcodec's FLAC encoder (tests/golden/make_golden_flac.py; the goldens travel),
+# and — where the OpenCV wheel's FFmpeg libraries exist — FFmpeg's decoder beside sfb_flac_decode on fresh material
+
+def test_streams_written_by_ffmpegs_encoder_decode_bit_for_bit(golden_dir):
+    import hashlib
+    gold = np.load(golden_dir/"flac_ffmpeg.npz")
+    names = sorted({key.rsplit(".", 1)[0] for key in gold.files})
+    assert len(names) == 16
+    for name in names:
+        rate, channels, bits, blocksize, frames = (int(v) for v in gold[f"{name}.format"])
+        info, pcm = decode(gold[f"{name}.stream"].tobytes())
+        assert (info.samplerate, info.channels, info.bits_per_sample, info.total_samples, info.has_md5) == (rate, channels, bits, frames, 1), name
+        assert pcm.shape == (frames, channels)
+        digest = hashlib.sha256(np.ascontiguousarray(pcm.astype(np.int32)).tobytes()).digest()
+        assert digest == gold[f"{name}.sha256"].tobytes(), name
+
+
+def test_read_flac_on_an_ffmpeg_stream(golden_dir, tmp_path):
+    """audio/reader.read_flac (what `ShaderAudio(file=...)` calls): float32 planar, scaled by 2^(bits-1)"""
+    gold = np.load(golden_dir/"flac_ffmpeg.npz")
+    (tmp_path/"clip.flac").write_bytes(gold["s24_stereo_level8.stream"].tobytes())
+    _, pcm = decode(gold["s24_stereo_level8.stream"].tobytes())
+    clip, rate = reader.read_flac(tmp_path/"clip.flac")
+    assert rate == 44100 and clip.dtype == np.float32 and np.array_equal(clip, (pcm.T/2.0**23).astype(np.float32))
+
+
+def _bridge():
+    from tests import avcodec_bridge as B
+    if not B.available():
+        pytest.skip("no FFmpeg libraries (OpenCV wheel) on this machine")
+    return B
+
+
+@pytest.mark.parametrize("bits,channels,blocksize,level,options", [
+    (16, 2, 4096, 3, {}), (16, 2, 1152, 9, dict(lpc_type="levinson", lpc_coeff_precision=12)), (16, 1, 4096, 8, dict(lpc_passes=2, lpc_type="cholesky")),
+    (24, 2, 4096, 10, {}), (24, 2, 576, 5, dict(ch_mode="indep")), (8, 1, 256, 5, {}), (32, 2, 2048, 8, {}), (12, 2, 4096, 5, {})])
+def test_fresh_material_through_ffmpegs_encoder(bits, channels, blocksize, level, options):
+    """Not the committed streams: new samples, encoded by FFmpeg now, decoded by both decoders"""
+    B = _bridge()
+    x = signal(2*blocksize + 333, channels, bits, seed=blocksize + level)
+    stream, held, held_bits = B.encode(x, bits=bits, blocksize=blocksize, level=level, **options)
+    info, pcm = decode(stream)
+    assert info.bits_per_sample == held_bits and info.has_md5 == 1
+    assert np.array_equal(pcm, held)
+    assert np.array_equal(B.decode(stream, channels, held_bits), held)
+
+
+@pytest.mark.parametrize("kind", ["constant", "verbatim", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "lpc1", "lpc2", "lpc8", "lpc32"])
+def test_ffmpegs_decoder_reads_the_test_encoders_streams_alike(kind):
+    """The other direction: what tests/flac_writer.py writes is FLAC to FFmpeg too, and means the same samples — so the
+    round trips above test sfb_flac_decode on valid streams, not on a private dialect"""
+    B = _bridge()
+    for bits, stereo, wasted in ((16, "independent", 0), (24, "mid_side", 0), (8, "left_side", 0), (16, "side_right", 3)):
+        x = signal(1500, 2, bits, seed=bits, wasted=wasted)
+        if kind == "constant":
+            x[:] = x[0]
+        stream = write_flac(x, bits=bits, blocksize=512, subframe=kind, stereo=stereo)
+        assert np.array_equal(B.decode(stream, 2, bits), x), (kind, bits, stereo)
+        assert np.array_equal(decode(stream)[1], x)
