@@ -29,6 +29,7 @@ import numpy as np
 
 P = ctypes.c_void_p
 _LIBS = None
+_LIBS_EXTRA = {}
 AV_SAMPLE_FMT_S16, AV_SAMPLE_FMT_S32 = 1, 2
 AV_OPT_SEARCH_CHILDREN = 1
 
@@ -56,7 +57,12 @@ def _load():
             found[stem] = ctypes.CDLL(hits[0], mode=ctypes.RTLD_GLOBAL)
         except OSError:
             return None
-    u, c, f = found["avutil"], found["avcodec"], found["avformat"]
+    u, c, f, r = found["avutil"], found["avcodec"], found["avformat"], found["swresample"]
+    r.swr_alloc.restype = P
+    r.swr_init.argtypes = [P]
+    r.swr_convert.argtypes = [P, P, ctypes.c_int, P, ctypes.c_int]
+    r.swr_free.argtypes = [ctypes.POINTER(P)]
+    u.av_opt_set_sample_fmt.argtypes = [P, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     c.avcodec_version.restype = ctypes.c_uint
     if not (59 <= (c.avcodec_version() >> 16) <= 62):              # the layouts read below were checked for FFmpeg 5 … 8
         return None
@@ -66,6 +72,7 @@ def _load():
     f.avformat_close_input.argtypes = [ctypes.POINTER(P)]
     for name in ("avcodec_find_decoder_by_name", "avcodec_find_encoder_by_name"):
         getattr(c, name).restype, getattr(c, name).argtypes = P, [ctypes.c_char_p]
+    c.avcodec_find_decoder.restype, c.avcodec_find_decoder.argtypes = P, [ctypes.c_int]
     c.avcodec_alloc_context3.restype, c.avcodec_alloc_context3.argtypes = P, [P]
     c.avcodec_parameters_to_context.argtypes = [P, P]
     c.avcodec_open2.argtypes = [P, P, P]
@@ -85,6 +92,7 @@ def _load():
     if not (c.avcodec_find_decoder_by_name(b"flac") and c.avcodec_find_encoder_by_name(b"flac")):
         return None
     _LIBS = (u, c, f)
+    _LIBS_EXTRA["swresample"] = r
     return _LIBS
 
 
@@ -101,8 +109,9 @@ def _u64(raw: bytes, at: int) -> int:
 
 
 class _Demuxed:
-    """An opened FLAC file: its only stream's codec parameters and a decoder on them"""
-    def __init__(self, path: str):
+    """An opened audio file: its only stream's codec parameters and a decoder on them (`codec`: the decoder expected,
+    by name; None = whatever the demuxer found)"""
+    def __init__(self, path: str, codec: str | None = "flac"):
         u, c, f = _load()
         self.fmt = P()
         if f.avformat_open_input(ctypes.byref(self.fmt), path.encode(), None, None) != 0:
@@ -118,12 +127,12 @@ class _Demuxed:
             raise RuntimeError("unexpected AVStream layout")
         self.codecpar = _u64(stream, 16)
         par = ctypes.string_at(self.codecpar, 8)
-        decoder = c.avcodec_find_decoder_by_name(b"flac")
-        if _u32(par, 0) != 1 or _u32(par, 4) != _u32(ctypes.string_at(decoder, 24), 20):    # AVMEDIA_TYPE_AUDIO, AV_CODEC_ID_FLAC
-            raise RuntimeError("unexpected AVCodecParameters layout")
+        decoder = c.avcodec_find_decoder_by_name(codec.encode()) if codec else c.avcodec_find_decoder(_u32(par, 4))
+        if _u32(par, 0) != 1 or not decoder or (codec and _u32(par, 4) != _u32(ctypes.string_at(decoder, 24), 20)):
+            raise RuntimeError("unexpected AVCodecParameters layout")        # AVMEDIA_TYPE_AUDIO, AVCodec.id of the named codec
         self.decoder = P(c.avcodec_alloc_context3(decoder))
         if c.avcodec_parameters_to_context(self.decoder, self.codecpar) != 0 or c.avcodec_open2(self.decoder, decoder, None) != 0:
-            raise RuntimeError("FFmpeg's FLAC decoder did not open")
+            raise RuntimeError("FFmpeg's decoder did not open")
         self.packet, self.frame = P(c.av_packet_alloc()), P(u.av_frame_alloc())
 
     def frames(self):
@@ -231,3 +240,40 @@ def encode(samples: np.ndarray, bits: int = 16, blocksize: int = 4096, rate: int
         finally:
             c.av_packet_free(ctypes.byref(packet)); c.avcodec_free_context(ctypes.byref(encoder)); source.close()
     return streaminfo(held, held_bits, blocksize, rate, frames) + b"".join(frames), held, held_bits
+
+
+def wav_as_f32le(path, channels: int, rate: int) -> np.ndarray:
+    """What `ffmpeg -i file.wav -f f32le -` delivers (the reference's BrokenAudioReader, ffmpeg.py:1279-1330): FFmpeg's
+    WAV demuxer + PCM decoder, then libswresample to packed float32. → (frames, channels) float32"""
+    u, c, f = _load()
+    r = _LIBS_EXTRA["swresample"]
+    source = _Demuxed(str(path), codec=None)
+    layout = {1: b"mono", 2: b"stereo"}[channels]
+    converters, blocks = {}, []
+    try:
+        for frame in source.frames():
+            head = ctypes.string_at(frame.value, 120)
+            count, fmt = _u32(head, 112), _u32(head, 116)
+            if not (0 < count <= (1 << 20)) or fmt > 4:              # u8, s16, s32, flt, dbl (packed): what PCM decoders emit
+                raise RuntimeError("unexpected AVFrame layout")
+            if fmt not in converters:
+                swr = P(r.swr_alloc())
+                for key in (b"in_chlayout", b"out_chlayout"):
+                    assert u.av_opt_set(swr, key, layout, 0) == 0
+                for key in (b"in_sample_rate", b"out_sample_rate"):
+                    assert u.av_opt_set_int(swr, key, rate, 0) == 0
+                assert u.av_opt_set_sample_fmt(swr, b"in_sample_fmt", fmt, 0) == 0
+                assert u.av_opt_set_sample_fmt(swr, b"out_sample_fmt", 3, 0) == 0           # AV_SAMPLE_FMT_FLT
+                assert r.swr_init(swr) == 0
+                converters[fmt] = swr
+            out = np.empty((count, channels), np.float32)
+            planes = (P*8)(out.ctypes.data)
+            done = r.swr_convert(converters[fmt], ctypes.cast(planes, P), count, frame, count)   # AVFrame starts with data[8]
+            if done != count:
+                raise RuntimeError(f"swr_convert returned {done} of {count}")
+            blocks.append(out)
+    finally:
+        for swr in converters.values():
+            r.swr_free(ctypes.byref(swr))
+        source.close()
+    return np.concatenate(blocks)

@@ -115,3 +115,31 @@ def test_audio_module_takes_a_wav_file(tmp_path):
     assert audio._wav is not None and audio._wav.format == N.PCM_S16
     audio.load(audio.clip, 44100)                              # an explicit clip replaces the file association
     assert audio._wav is None
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,tag,bits", CASES)
+@pytest.mark.parametrize("channels", [1, 2])
+def test_wav_formats_decode_like_the_real_libswresample(tmp_path, name, tag, bits, channels):
+    """The same files through FFmpeg itself — WAV demuxer, pcm_* decoder, libswresample to packed float32: what the
+    reference's `ffmpeg -f f32le` child writes into its pipe (ffmpeg.py:1279-1287). From the OpenCV wheel's libraries
+    (tests/avcodec_bridge.py); the rules restated in the test above are thereby pinned to the library they restate"""
+    from tests import avcodec_bridge as B
+    if not B.available():
+        pytest.skip("no FFmpeg libraries (OpenCV wheel) on this machine")
+    rng = np.random.default_rng(100 + bits + channels)
+    frames = 5000
+    if tag == 3:
+        data = rng.uniform(-1.5, 1.5, (frames, channels))
+        data[:4, 0] = (0.0, -0.0, 1e-40, 3.0000001)                    # a denormal after the cast, a value past full scale
+    elif bits == 8:
+        data = rng.integers(0, 256, (frames, channels)); data[:3, 0] = (0, 128, 255)
+    else:
+        lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+        data = rng.integers(lo, hi + 1, (frames, channels)); data[:5, 0] = (lo, hi, 0, -1, 16777217 if bits == 32 else 1)
+    path = tmp_path/f"{name}.wav"
+    write_wav(path, data, 44100, tag, bits, junk=(channels == 2))
+    want = B.wav_as_f32le(path, channels, 44100)
+    pcm, rate = R.read_wav(path)
+    assert want.shape == (frames, channels) and rate == 44100
+    assert np.array_equal(pcm.T.view(np.uint32), want.view(np.uint32))         # bit patterns: -0.0 and denormals included

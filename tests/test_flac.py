@@ -152,6 +152,7 @@ def _bridge():
     return B
 
 
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("bits,channels,blocksize,level,options", [
     (16, 2, 4096, 3, {}), (16, 2, 1152, 9, dict(lpc_type="levinson", lpc_coeff_precision=12)), (16, 1, 4096, 8, dict(lpc_passes=2, lpc_type="cholesky")),
     (24, 2, 4096, 10, {}), (24, 2, 576, 5, dict(ch_mode="indep")), (8, 1, 256, 5, {}), (32, 2, 2048, 8, {}), (12, 2, 4096, 5, {})])
@@ -166,6 +167,7 @@ def test_fresh_material_through_ffmpegs_encoder(bits, channels, blocksize, level
     assert np.array_equal(B.decode(stream, channels, held_bits), held)
 
 
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("kind", ["constant", "verbatim", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "lpc1", "lpc2", "lpc8", "lpc32"])
 def test_ffmpegs_decoder_reads_the_test_encoders_streams_alike(kind):
     """The other direction: what tests/flac_writer.py writes is FLAC to FFmpeg too, and means the same samples — so the
