@@ -107,3 +107,45 @@ def test_video_scene_from_a_compressed_file_shows_the_decoded_frames(tmp_path):
     assert isinstance(scene.video._reader, video.CodecFrames)
     for k in (1, 3, 5):                                   # same fps: frame k shows clip frame k-1 (strict > at t = 0)
         assert np.array_equal(shown[k], np.flipud(clip[k - 1])), k
+
+
+def test_screen_space_derivatives():
+    """dFdx / dFdy / fwidth: differences inside the 2 x 2 quads the lanes of a warp shade. Varyings are affine over the
+    target, so their derivatives are known in closed form — per fragment in the screen pass, per fragment as well in the
+    fused pass (the neighbouring lane is S fragments away and the difference is scaled back)"""
+    from oracle import glsl_np as G
+    from shaderflow_b200 import _native as N, glsl
+    from tests import jit_cases as J
+    from tests.helpers import native_uniforms
+    ctx = N.Context(0)
+    text = """void main() {
+        float edge = length(gluv) - 0.6;
+        fragColor = vec4(dFdx(stxy.x), dFdy(stxy.y), fwidth(agluv.x + agluv.y), smoothstep(-fwidth(edge), fwidth(edge), edge));
+        vec2 both = dFdx(astuv) + dFdy(astuv);
+        fragColor.xy += 1000.0*both;
+    }"""
+    image, translation, _ = glsl.build(text, J.HEADER)
+    scene = ctx.program_load(image, 0)
+    info = dict(extra=[], samplers=[])
+    W, H, S = 48, 28, 2
+    for Wr, Hr in ((W, H), (W*S, H*S)):
+        u = G.Uniforms(iResolution=(W, H), iWantAspect=W/H, iSSAA=Wr/W)
+        f32 = torch.zeros((Hr, Wr, 4), dtype=torch.float32, device="cuda")
+        rgba = torch.zeros((Hr, Wr, 4), dtype=torch.uint8, device="cuda")
+        ctx.render_screen(scene, native_uniforms(u, info), [], Wr, Hr, rgba, f32, 0)
+        ctx.sync()
+        got = f32.cpu().numpy()
+        assert np.allclose(got[..., 0], W/Wr + 1000.0/Wr, rtol=1e-4) and np.allclose(got[..., 1], H/Hr + 1000.0/Hr, rtol=1e-4)
+        assert np.allclose(got[..., 2], 2.0/Wr + 2.0/Hr, rtol=1e-4)
+        edge = got[..., 3]
+        assert edge.min() == 0.0 and edge.max() == 1.0 and ((edge > 0.01) & (edge < 0.99)).mean() < 0.12      # a thin antialiased ring
+    # the fused pass: same derivatives per fragment although neighbouring lanes shade neighbouring OUTPUT pixels
+    u = G.Uniforms(iResolution=(W, H), iWantAspect=W/H, iSSAA=float(S))
+    probe = torch.zeros((H*S, W*S, 4), dtype=torch.float32, device="cuda")
+    frame = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.render_frame_probe(scene, native_uniforms(u, info), [], W, H, S, S, 3, frame, probe, 0)
+    ctx.sync()
+    got = probe.cpu().numpy()
+    assert np.allclose(got[..., 0], 0.5 + 1000.0/(W*S), rtol=1e-4) and np.allclose(got[..., 2], 2.0/(W*S) + 2.0/(H*S), rtol=1e-4)
+    ctx.program_unload(scene)
+    ctx.destroy()
