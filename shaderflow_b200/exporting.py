@@ -4,7 +4,9 @@ The reference reads the GL framebuffer into a ring of mapped buffers and lets tu
 ffmpeg child (exporting.py:140-174). Here the ring lives in libsfb200 (sfb_pipe_*: device frames +
 pinned host mirrors + a writer thread); the kernels render straight into the ring's device frame.
 Sinks: an ffmpeg child when the binary exists (same rawvideo rgb24 + vflip contract, exporting.py:94-103),
-a raw .rgb file, bytes, or a null sink that still pays the device→host copy."""
+a raw .rgb file, bytes, or a null sink that still pays the device→host copy. Without an ffmpeg binary a video file
+is still written when the opencv package is installed: an in-process encoder thread (the libavcodec inside the
+OpenCV wheel) takes the child's place at the other end of a pipe — same bytes on the wire, same vflip."""
 from __future__ import annotations
 
 import os
@@ -33,6 +35,73 @@ class OutputType(str, Enum):
     TCP = "tcp"
 
 
+class InProcessEncoder:
+    """Stands where the ffmpeg child stands when there is no ffmpeg binary: reads rawvideo rgb24 frames (bottom row
+    first) from a pipe, flips them (the child's `-vf vflip`) and encodes them with `cv2.VideoWriter` — FFmpeg's
+    libavcodec / libavformat as bundled by the OpenCV wheel. Codec by container: lossless FFV1 for .mkv, Motion-JPEG
+    for .avi, MPEG-4 for everything else (the wheel carries no H.264 encoder). Video only: audio is not muxed."""
+    CODECS = {".mkv": "FFV1", ".avi": "MJPG"}
+
+    def __init__(self, path: Path, width: int, height: int, fps: float):
+        import threading
+        import cv2
+        self.path, self.width, self.height, self.frames, self.error = Path(path), width, height, 0, None
+        fourcc = self.CODECS.get(self.path.suffix.lower(), "mp4v")
+        self.writer = cv2.VideoWriter(str(self.path), cv2.VideoWriter_fourcc(*fourcc), float(fps), (width, height))
+        if not self.writer.isOpened():
+            raise RuntimeError(f"OpenCV cannot encode '{self.path}' ({fourcc})")
+        self.read_fd, self.write_fd = os.pipe()
+        try:
+            import fcntl
+            fcntl.fcntl(self.write_fd, 1031, 1 << 20)          # F_SETPIPE_SZ: fewer wake-ups per 25 MB frame
+        except Exception:
+            pass
+        self.thread = threading.Thread(target=self._run, name="sfb-encoder", daemon=True)
+        self.thread.start()
+
+    @staticmethod
+    def available() -> bool:
+        import importlib.util
+        return importlib.util.find_spec("cv2") is not None
+
+    def _run(self) -> None:
+        import numpy as np
+        size = self.width*self.height*3
+        frame = np.empty(size, np.uint8)
+        view = memoryview(frame)
+        try:
+            with os.fdopen(self.read_fd, "rb", buffering=0) as source:
+                while True:
+                    got = 0
+                    while got < size:
+                        n = source.readinto(view[got:])
+                        if not n:
+                            break
+                        got += n
+                    if got < size:
+                        break                                   # the writer closed its end (a partial frame is dropped)
+                    image = frame.reshape(self.height, self.width, 3)[::-1, :, ::-1]     # vflip, rgb → bgr
+                    self.writer.write(np.ascontiguousarray(image))
+                    self.frames += 1
+        except Exception as error:                              # surfaced by ExportingHelper.check_process
+            self.error = error
+        finally:
+            self.writer.release()
+
+    def poll(self) -> None:
+        if self.error is not None:
+            raise RuntimeError(f"The in-process encoder stopped: {self.error}")
+
+    def close(self) -> int:
+        """The last frame has been written to the pipe: close it, wait for the encoder, → frames encoded"""
+        if self.write_fd is not None:
+            os.close(self.write_fd)
+            self.write_fd = None
+        self.thread.join()
+        self.poll()
+        return self.frames
+
+
 @define
 class ExportingHelper:
     scene: "ShaderScene"
@@ -51,6 +120,7 @@ class ExportingHelper:
     took: Optional[float] = None
     _file: Any = None
     _target: Optional[int] = None
+    encoder: Optional[InProcessEncoder] = None
 
     pipe_output = property(lambda self: self.type is OutputType.PIPE)
     path_output = property(lambda self: self.type is OutputType.PATH)
@@ -126,10 +196,16 @@ class ExportingHelper:
                 if self.type is OutputType.PIPE:     # raw rgb24 bytes instead of an encoded stream
                     self._file = tempfile.TemporaryFile(mode="w+b")
                     fd = self._file.fileno()
+                elif InProcessEncoder.available():
+                    s = self.scene
+                    if any(module.ffhook(self) for module in s.modules):
+                        logger.warn("No ffmpeg binary: the in-process encoder writes video only, the audio is not muxed")
+                    self.encoder = InProcessEncoder(self.output, s.width, s.height, s.fps)
+                    fd = self.encoder.write_fd
                 else:
                     raise RuntimeError(logger.error(
-                        f"No ffmpeg binary on PATH to encode '{self.output}'. Export raw frames with "
-                        "output='frames.rgb', bytes with output='pipe', or discard them with output='null'"))
+                        f"No ffmpeg binary on PATH (nor the opencv package) to encode '{self.output}'. Export raw frames "
+                        "with output='frames.rgb', bytes with output='pipe', or discard them with output='null'"))
             else:
                 self.stderr, self.stdout = tempfile.TemporaryFile(mode="r+b"), tempfile.TemporaryFile(mode="r+b")
                 self.process = subprocess.Popen(self.ffmpeg_command(), stdin=subprocess.PIPE,
@@ -139,6 +215,8 @@ class ExportingHelper:
         return fd
 
     def check_process(self) -> None:
+        if self.encoder is not None:
+            self.encoder.poll()
         if self.process is not None and self.process.poll() is not None:
             self.stderr.seek(0)
             raise RuntimeError("FFmpeg process closed unexpectedly with traceback:\n" + self.stderr.read().decode("utf-8"))
@@ -153,6 +231,10 @@ class ExportingHelper:
             self.process.kill()
             self.process.wait()
             self.process = None
+        if self.encoder is not None:
+            try: self.encoder.close()
+            except Exception: pass
+            self.encoder = None
         if self._file is not None:
             try: self._file.close()
             except Exception: pass
@@ -213,6 +295,9 @@ class ExportingHelper:
             self.process.stdin.close()
             self.process.wait()
             self.stdout.seek(0)
+        if self.encoder is not None:
+            self.encoder.close()
+            self.encoder = None
         if self._file is not None and self.type is OutputType.RAW:
             self._file.close()
         if self.bar is not None:

@@ -149,3 +149,29 @@ def test_screen_space_derivatives():
     assert np.allclose(got[..., 0], 0.5 + 1000.0/(W*S), rtol=1e-4) and np.allclose(got[..., 2], 2.0/(W*S) + 2.0/(H*S), rtol=1e-4)
     ctx.program_unload(scene)
     ctx.destroy()
+
+
+def test_export_to_a_video_file_without_an_ffmpeg_binary(tmp_path):
+    """output='x.mkv' with no ffmpeg on the box: the in-process encoder (exporting.InProcessEncoder, lossless FFV1 for
+    .mkv) sits at the other end of the sink's pipe — the decoded file holds the frames of the raw export, flipped to
+    top row first like the child's `-vf vflip` would"""
+    import shutil
+    cv2 = pytest.importorskip("cv2")
+    if shutil.which("ffmpeg"):
+        pytest.skip("an ffmpeg binary takes precedence over the in-process encoder")
+    import examples.demo as demo
+    W, H, frames = 96, 54, 12
+    scene = demo.ShaderToy()
+    flags = dict(width=W, height=H, ssaa=1, subsample=1, fps=60.0, time=frames/60)
+    raw = np.frombuffer(scene.main(output=bytes, **flags), np.uint8).reshape(frames, H, W, 3)
+    path = scene.main(output=tmp_path/"out.mkv", **flags)
+    assert path == tmp_path/"out.mkv" and path.stat().st_size > 0
+    capture = cv2.VideoCapture(str(path))
+    for k in range(frames):
+        ok, bgr = capture.read()
+        assert ok, k
+        assert np.array_equal(bgr[..., ::-1], raw[k][::-1]), k
+    assert not capture.read()[0]
+    # and the scene exports again afterwards (the ring went back to no descriptor)
+    again = np.frombuffer(scene.main(output=bytes, **flags), np.uint8)
+    assert np.array_equal(again, raw.reshape(-1))

@@ -131,3 +131,32 @@ def test_compressed_files_decode_through_opencv_when_there_is_no_ffmpeg(tmp_path
     scene.video._reader.frame(2)
     scene.main(width=64, height=36, fps=60.0, time=0.1)
     assert scene.video._reader.position == 0 and scene.video._frames == 3
+
+
+def test_in_process_encoder_stands_in_for_the_ffmpeg_child(tmp_path):
+    """exporting.InProcessEncoder: rawvideo rgb24 frames, bottom row first, written to its pipe — what the sink's writer
+    thread sends an ffmpeg child — come out as a video file whose frames are the export's, top row first. Lossless
+    container → byte for byte; MPEG-4 / Motion-JPEG → close. A partial last frame is dropped"""
+    import os
+    cv2 = pytest.importorskip("cv2")
+    from shaderflow_b200.exporting import InProcessEncoder
+    clip = synthetic.video_frames(64, 36, 6)                               # top row first
+    for name, exact in (("out.mkv", True), ("out.mp4", False), ("out.avi", False)):
+        encoder = InProcessEncoder(tmp_path/name, 64, 36, 30.0)
+        for frame in clip:
+            wire = np.ascontiguousarray(frame[::-1]).tobytes()             # the export's row order
+            at = 0
+            while at < len(wire):                                          # in pieces, like a pipe delivers them
+                at += os.write(encoder.write_fd, wire[at:at + 5000])
+        os.write(encoder.write_fd, b"\x00"*100)
+        assert encoder.close() == 6
+        capture = cv2.VideoCapture(str(tmp_path/name))
+        assert capture.get(cv2.CAP_PROP_FPS) == 30.0 and int(capture.get(cv2.CAP_PROP_FRAME_WIDTH)) == 64
+        for k, frame in enumerate(clip):
+            ok, bgr = capture.read()
+            assert ok, (name, k)
+            error = np.abs(bgr[..., ::-1].astype(int) - frame.astype(int))
+            assert (error.max() == 0) if exact else (error.mean() < 12), (name, k, error.max(), error.mean())
+        assert not capture.read()[0]
+    with pytest.raises(RuntimeError, match="cannot encode"):
+        InProcessEncoder(tmp_path/"no_such_dir"/"out.mp4", 64, 36, 30.0)
