@@ -40,7 +40,7 @@ class AudioMode(Enum):
 
 def read_audio_file(path: Path) -> tuple[np.ndarray, int]:
     """→ (pcm float32 (channels, samples), samplerate). RIFF/WAVE and FLAC natively (audio/reader.py), anything else
-    through ffmpeg when a binary exists"""
+    through ffmpeg when a binary exists, else through FFmpeg's libraries in process (audio/avcodec.py)"""
     path = Path(path)
     if path.suffix.lower() in (".wav", ".wave", ".rf64"):
         from shaderflow_b200.audio.reader import read_wav
@@ -50,7 +50,11 @@ def read_audio_file(path: Path) -> tuple[np.ndarray, int]:
         return read_flac(path)
     ffmpeg, ffprobe = shutil.which("ffmpeg"), shutil.which("ffprobe")
     if not (ffmpeg and ffprobe):
-        raise RuntimeError(f"Decoding '{path}' needs ffmpeg/ffprobe on PATH; load WAV files or call load(pcm, samplerate)")
+        from shaderflow_b200.audio import avcodec
+        if avcodec.available():                  # the same libavcodec / libswresample, in process (OpenCV wheel)
+            return avcodec.decode_file(path)
+        raise RuntimeError(f"Decoding '{path}' needs ffmpeg/ffprobe on PATH or the opencv package; load WAV / FLAC files "
+                           "or call load(pcm, samplerate)")
     probe = subprocess.run([ffprobe, "-v", "error", "-select_streams", "a:0", "-show_entries",
         "stream=channels,sample_rate", "-of", "csv=p=0", str(path)], capture_output=True, text=True, check=True)
     rate, channels = [int(x) for x in probe.stdout.strip().split(",")][:2]

@@ -143,3 +143,41 @@ def test_wav_formats_decode_like_the_real_libswresample(tmp_path, name, tag, bit
     pcm, rate = R.read_wav(path)
     assert want.shape == (frames, channels) and rate == 44100
     assert np.array_equal(pcm.T.view(np.uint32), want.view(np.uint32))         # bit patterns: -0.0 and denormals included
+
+
+@pytest.mark.timeout(120)
+def test_other_audio_files_decode_through_ffmpegs_libraries_in_process(tmp_path, golden_dir):
+    """audio/avcodec.decode_file — what `ShaderAudio(file='song.opus')` falls to without an ffmpeg binary: demuxer →
+    decoder → libswresample → planar float32. Held to the native readers on the formats both can read (packed s16 / s24 /
+    f32 from WAV, FLAC as packed and — through the decoder's request_sample_fmt — as PLANAR samples, the layout lossy
+    codecs deliver), and refused cleanly on files without audio"""
+    from shaderflow_b200.audio import avcodec
+    from shaderflow_b200.audio.module import read_audio_file
+    if not avcodec.available():
+        pytest.skip("no FFmpeg libraries (OpenCV wheel) on this machine")
+    rng = np.random.default_rng(8)
+    for name, tag, bits in (("s16", 1, 16), ("s24", 1, 24), ("f32", 3, 32)):
+        data = rng.uniform(-1, 1, (3000, 2)) if tag == 3 else rng.integers(-(1 << (bits - 1)), 1 << (bits - 1), (3000, 2))
+        write_wav(tmp_path/f"{name}.wav", data, 22050, tag, bits)
+        pcm, rate = avcodec.decode_file(tmp_path/f"{name}.wav")
+        want, _ = R.read_wav(tmp_path/f"{name}.wav")
+        assert rate == 22050 and pcm.dtype == np.float32 and pcm.flags.c_contiguous and np.array_equal(pcm, want)
+    gold = np.load(golden_dir/"flac_ffmpeg.npz")
+    for name, planar in (("s16_stereo_level8", None), ("s16_stereo_level8", "s16p"), ("s24_stereo_level8", "s32p"), ("s16_mono_level8", None), ("s16_48k", "s16p")):
+        (tmp_path/"clip.flac").write_bytes(gold[f"{name}.stream"].tobytes())
+        want, want_rate = R.read_flac(tmp_path/"clip.flac")
+        # an unknown suffix: the dispatcher cannot use the native reader
+        (tmp_path/"clip.oga").write_bytes(gold[f"{name}.stream"].tobytes())
+        pcm, rate = avcodec.decode_file(tmp_path/"clip.oga", dict(request_sample_fmt=planar) if planar else None)
+        assert rate == want_rate and np.array_equal(pcm, want), (name, planar)
+    import shutil
+    if not (shutil.which("ffmpeg") and shutil.which("ffprobe")):
+        pcm, rate = read_audio_file(tmp_path/"clip.oga")
+        assert rate == 48000 and np.array_equal(pcm, want)
+    cv2 = pytest.importorskip("cv2")
+    writer = cv2.VideoWriter(str(tmp_path/"silent.avi"), cv2.VideoWriter_fourcc(*"MJPG"), 10.0, (16, 16))
+    writer.write(np.zeros((16, 16, 3), np.uint8)); writer.release()
+    with pytest.raises(RuntimeError, match="no audio stream"):
+        avcodec.decode_file(tmp_path/"silent.avi")
+    with pytest.raises(RuntimeError, match="cannot open"):
+        avcodec.decode_file(tmp_path/"missing.opus")
