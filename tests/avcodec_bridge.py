@@ -8,7 +8,8 @@ with the `flac` encoder and decoder compiled in. They are driven here through ct
                                           partitioning, stereo decorrelation and wasted-bits detection — what real files
                                           contain), framed by a STREAMINFO block built here (with the MD5 of the samples)
 
-There are no FFmpeg headers in the image, so no struct is ever WRITTEN: codec contexts are configured through
+There are no FFmpeg headers in the image, so (with one checked exception in transcode(), for encoders other than FLAC) no
+struct is ever WRITTEN: codec contexts are configured through
 avcodec_parameters_to_context + AVOptions, and the encoder is fed the very AVFrames FFmpeg's decoder produced from a
 verbatim-coded stream of the samples (tests/flac_writer.py). The few fields that are READ sit at the start of their
 structs and have not moved since FFmpeg 5 — AVFormatContext.nb_streams / .streams, AVStream.codecpar, AVFrame.data[0] /
@@ -191,35 +192,37 @@ def streaminfo(samples: np.ndarray, bits: int, blocksize: int, rate: int, frames
     return b"fLaC" + bytes([0x80]) + len(body).to_bytes(3, "big") + body
 
 
-def encode(samples: np.ndarray, bits: int = 16, blocksize: int = 4096, rate: int = 44100, level: int = 5, **private) -> tuple[bytes, np.ndarray, int]:
-    """(frames, channels) ints → (FLAC stream by FFmpeg's encoder, the samples it holds, their bit depth).
-
-    The encoder's input is what FFmpeg's decoder makes of a verbatim-coded stream of `samples`, so 8-bit material
-    arrives left-justified in 16 bits (the stream is 16-bit with 8 wasted bits) and 20-bit material in 24 — hence the
-    returned samples / depth.
-    `private` are the encoder's own AVOptions (lpc_type, lpc_passes, ch_mode, min_partition_order, …)."""
+def transcode(samples: np.ndarray, codec: str, bits: int, blocksize: int, rate: int, settings: dict, sync=None) -> list[bytes]:
+    """The packets FFmpeg's encoder `codec` makes of `samples`: a verbatim FLAC stream of them (tests/flac_writer.py) is
+    decoded by FFmpeg and the decoder's AVFrames go straight into the encoder, whose context is configured from the
+    demuxed stream's parameters + `settings` (AVOptions). `sync(packet)` sanity-checks the packet layout read here"""
     from tests.flac_writer import write_flac
     u, c, f = _load()
-    samples = np.asarray(samples, np.int64)
-    held_bits = 16 if bits <= 16 else (24 if bits <= 24 else 32)       # flacenc.c: S16 input is 16-bit, S32 is 24-bit or 32-bit
-    held = samples << (held_bits - bits)
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "verbatim.flac")
         Path(path).write_bytes(write_flac(samples, rate=rate, bits=bits, blocksize=blocksize, subframe="verbatim"))
         source = _Demuxed(path)
-        encoder_kind = c.avcodec_find_encoder_by_name(b"flac")
+        encoder_kind = c.avcodec_find_encoder_by_name(codec.encode())
         encoder = P(c.avcodec_alloc_context3(encoder_kind))
         packet = P(c.av_packet_alloc())
         frames: list[bytes] = []
         try:
             if c.avcodec_parameters_to_context(encoder, source.codecpar) != 0:
                 raise RuntimeError("encoder parameters")
-            settings = dict(time_base=f"1/{rate}", frame_size=blocksize, compression_level=level, strict=-2, **private)
+            if codec != "flac":
+                # the parameters carried FLAC's codec id along. The one write into an FFmpeg struct in this file:
+                # AVCodecContext.codec_id (after av_class, log_level_offset, codec_type, codec — unchanged since FFmpeg 1),
+                # made only where the field demonstrably is: it must hold FLAC's id, next to codec_type = audio
+                head = ctypes.string_at(encoder.value, 28)
+                flac_id = _u32(ctypes.string_at(c.avcodec_find_decoder_by_name(b"flac"), 24), 20)
+                if _u32(head, 12) != 1 or _u32(head, 24) != flac_id:
+                    raise RuntimeError("unexpected AVCodecContext layout")
+                ctypes.memmove(encoder.value + 24, ctypes.string_at(encoder_kind, 24)[20:24], 4)
             for key, value in settings.items():
                 if u.av_opt_set(encoder, key.encode(), str(value).encode(), AV_OPT_SEARCH_CHILDREN) != 0:
-                    raise RuntimeError(f"FFmpeg's FLAC encoder has no option {key}={value}")
+                    raise RuntimeError(f"FFmpeg's {codec} encoder has no option {key}={value}")
             if c.avcodec_open2(encoder, encoder_kind, None) != 0:
-                raise RuntimeError("FFmpeg's FLAC encoder did not open")
+                raise RuntimeError(f"FFmpeg's {codec} encoder did not open")
 
             def pull():
                 while c.avcodec_receive_packet(encoder, packet) == 0:
@@ -227,18 +230,33 @@ def encode(samples: np.ndarray, bits: int = 16, blocksize: int = 4096, rate: int
                     data, size = _u64(head, 24), _u32(head, 32)              # AVPacket.data / .size
                     if size:
                         block = ctypes.string_at(data, size)
-                        if block[0] != 0xFF or (block[1] & 0xFC) != 0xF8:    # every FLAC frame starts with the sync code
+                        if sync is not None and not sync(block):
                             raise RuntimeError("unexpected AVPacket layout")
                         frames.append(block)
                     c.av_packet_unref(packet)
             for frame in source.frames():
                 if c.avcodec_send_frame(encoder, frame) != 0:
-                    raise RuntimeError("FFmpeg's FLAC encoder refused a frame")
+                    raise RuntimeError(f"FFmpeg's {codec} encoder refused a frame")
                 pull()
             c.avcodec_send_frame(encoder, None)
             pull()
         finally:
             c.av_packet_free(ctypes.byref(packet)); c.avcodec_free_context(ctypes.byref(encoder)); source.close()
+    return frames
+
+
+def encode(samples: np.ndarray, bits: int = 16, blocksize: int = 4096, rate: int = 44100, level: int = 5, **private) -> tuple[bytes, np.ndarray, int]:
+    """(frames, channels) ints → (FLAC stream by FFmpeg's encoder, the samples it holds, their bit depth).
+
+    The encoder's input is what FFmpeg's decoder makes of a verbatim-coded stream of `samples`, so 8-bit material
+    arrives left-justified in 16 bits (the stream is 16-bit with 8 wasted bits) and 20-bit material in 24 — hence the
+    returned samples / depth.
+    `private` are the encoder's own AVOptions (lpc_type, lpc_passes, ch_mode, min_partition_order, …)."""
+    samples = np.asarray(samples, np.int64)
+    held_bits = 16 if bits <= 16 else (24 if bits <= 24 else 32)       # flacenc.c: S16 input is 16-bit, S32 is 24-bit or 32-bit
+    held = samples << (held_bits - bits)
+    settings = dict(time_base=f"1/{rate}", frame_size=blocksize, compression_level=level, strict=-2, **private)
+    frames = transcode(samples, "flac", bits, blocksize, rate, settings, sync=lambda block: block[0] == 0xFF and (block[1] & 0xFC) == 0xF8)
     return streaminfo(held, held_bits, blocksize, rate, frames) + b"".join(frames), held, held_bits
 
 

@@ -181,3 +181,34 @@ def test_other_audio_files_decode_through_ffmpegs_libraries_in_process(tmp_path,
         avcodec.decode_file(tmp_path/"silent.avi")
     with pytest.raises(RuntimeError, match="cannot open"):
         avcodec.decode_file(tmp_path/"missing.opus")
+
+
+@pytest.mark.timeout(120)
+def test_a_lossy_file_decodes_end_to_end(tmp_path):
+    """An MPEG-1 Layer II file, written here by FFmpeg's own encoder (tests/avcodec_bridge.transcode; its packets are
+    self-framing, so their concatenation is the file), read through `ShaderAudio(file=...)`'s dispatcher: rate, channels
+    and length are the stream's, and the samples are the original tones behind the codec's 481-sample delay"""
+    import shutil
+    from tests import avcodec_bridge as B
+    from shaderflow_b200.audio import avcodec
+    from shaderflow_b200.audio.module import BrokenAudio
+    if not (B.available() and avcodec.available()):
+        pytest.skip("no FFmpeg libraries (OpenCV wheel) on this machine")
+    if shutil.which("ffmpeg") and shutil.which("ffprobe"):
+        pytest.skip("an ffmpeg binary takes precedence")
+    rate, n = 44100, 1152*20
+    t = np.arange(n)/rate
+    tones = np.stack([0.5*np.sin(2*np.pi*440*t) + 0.2*np.sin(2*np.pi*1330*t), 0.4*np.sin(2*np.pi*660*t)], 1)
+    pcm = np.rint(tones*32767).astype(np.int64)
+    packets = B.transcode(pcm, "mp2", 16, 1152, rate, dict(time_base=f"1/{rate}", b=192000),
+                          sync=lambda p: p[0] == 0xFF and (p[1] & 0xE0) == 0xE0)
+    assert len(packets) == 20
+    (tmp_path/"tones.mp2").write_bytes(b"".join(packets))
+    audio = BrokenAudio()
+    audio.file = tmp_path/"tones.mp2"
+    assert audio.samplerate == rate and audio.channels == 2 and audio.clip.dtype == np.float32
+    assert audio.total_samples == n and audio.duration == pytest.approx(n/rate)
+    lag = 481                                                          # MPEG audio Layer II: 480 + 1 samples
+    want = (pcm/32768).T[:, :n - 2000]
+    error = audio.clip[:, lag:lag + n - 2000] - want
+    assert 10*np.log10((want**2).mean()/(error**2).mean()) > 30        # 192 kb/s: ≈ 36 dB on these tones
