@@ -160,3 +160,42 @@ def test_in_process_encoder_stands_in_for_the_ffmpeg_child(tmp_path):
         assert not capture.read()[0]
     with pytest.raises(RuntimeError, match="cannot encode"):
         InProcessEncoder(tmp_path/"no_such_dir"/"out.mp4", 64, 36, 30.0)
+
+
+def test_yuv_rule_against_ffmpegs_swscale(tmp_path):
+    """What a Y4M clip looks like through the reference is libswscale's yuv420p → rgb24 (its ffmpeg child, default flags:
+    integer tables, chroma replicated 2 x 2, no accurate rounding). sfb_video_frame computes BT.601 in float32 instead
+    (tests/test_gpu_video.py holds the kernel to this formula within 1 LSB). The distance between the two, measured on
+    the real library: at most 3 codes, 1.1 on average — swscale's fast path carries a bias of about one code; the float
+    rule is the one closer to the RGB the clip was made from."""
+    import ctypes, glob, importlib.util
+    from pathlib import Path
+    cv2 = pytest.importorskip("cv2")
+    from tests.test_gpu_video import yuv_to_rgb
+    site = Path(list(importlib.util.find_spec("cv2").submodule_search_locations)[0]).parent
+    hits = [h for d in ("opencv_python_headless.libs", "opencv_python.libs") for h in glob.glob(str(site/d/"libswscale-*.so*"))]
+    if not hits:
+        pytest.skip("no libswscale in the OpenCV wheel")
+    sws, P = ctypes.CDLL(hits[0]), ctypes.c_void_p
+    sws.sws_getContext.restype, sws.sws_getContext.argtypes = P, [ctypes.c_int]*7 + [P, P, P]
+    sws.sws_scale.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, P, P]
+    sws.sws_freeContext.argtypes = [P]
+    W, H = 320, 180
+    clip = synthetic.video_frames(W, H, 2)
+    synthetic.write_y4m(tmp_path/"clip.y4m", clip, fps=30, colorspace="420jpeg")
+    info = video.parse_y4m(tmp_path/"clip.y4m")
+    planes = np.asarray(video.FileFrames(tmp_path/"clip.y4m", info).frame(1))
+    y = planes[:W*H].reshape(H, W).copy()
+    u = planes[W*H:W*H + W*H//4].reshape(H//2, W//2).copy()
+    v = planes[W*H + W*H//4:].reshape(H//2, W//2).copy()
+    ours = yuv_to_rgb(y, np.repeat(np.repeat(u, 2, 0), 2, 1), np.repeat(np.repeat(v, 2, 0), 2, 1), False)
+    context = sws.sws_getContext(W, H, 0, W, H, 2, 4, None, None, None)        # AV_PIX_FMT_YUV420P → RGB24, SWS_BICUBIC
+    theirs = np.zeros((H, W, 3), np.uint8)
+    src, src_stride = (P*4)(y.ctypes.data, u.ctypes.data, v.ctypes.data, None), (ctypes.c_int*4)(W, W//2, W//2, 0)
+    dst, dst_stride = (P*4)(theirs.ctypes.data, None, None, None), (ctypes.c_int*4)(W*3, 0, 0, 0)
+    assert sws.sws_scale(context, src, src_stride, 0, H, dst, dst_stride) == H
+    sws.sws_freeContext(context)
+    distance = np.abs(ours.astype(int) - theirs.astype(int))
+    assert distance.max() <= 3 and distance.mean() < 1.3
+    source = clip[1].astype(int)
+    assert np.abs(ours - source).mean() <= np.abs(theirs - source).mean()
