@@ -1448,6 +1448,36 @@ class Machine:
         d = self._dot(b, a)
         return V(t, (a - F32(2)*d[:, None]*b).astype(F32))
 
+    def b_refract(self, i, n, eta):                        # GLSL 3.30 §8.4: k = 1 − η²(1 − (n·i)²); 0 when k < 0
+        (a, b), t = self.gen(i, n)
+        e = self.fl(eta)[0].astype(F32)
+        d = self._dot(b, a)
+        k = (F32(1) - e*e*(F32(1) - d*d).astype(F32)).astype(F32)
+        with np.errstate(invalid="ignore"):
+            bent = ((e[:, None]*a).astype(F32) - ((e*d).astype(F32) + np.sqrt(k).astype(F32)).astype(F32)[:, None]*b).astype(F32)
+        return V(t, np.where((k < 0)[:, None], F32(0), bent).astype(F32))
+
+    def b_faceforward(self, n, i, nref):
+        (a, b, c), t = self.gen(n, i, nref)
+        return V(t, np.where((self._dot(c, b) < 0)[:, None], a, -a).astype(F32))
+
+    def _bits(self, x, src, dst, base):
+        _, n = vec_info(x.t)
+        return V(make_type(base, n), np.ascontiguousarray(x.a.astype(src)).view(dst))
+
+    def b_floatBitsToInt(self, x): return self._bits(x, F32, I32, "int")
+    def b_floatBitsToUint(self, x): return self._bits(x, F32, U32, "uint")
+    def b_intBitsToFloat(self, x): return self._bits(x, I32, F32, "float")
+    def b_uintBitsToFloat(self, x): return self._bits(x, U32, F32, "float")
+
+    def b_outerProduct(self, c, r):                        # column j = c·r[j]; square results only (mat2 / mat3 / mat4)
+        a, b = self.fl(c)[0], self.fl(r)[0]
+        if a.shape[1] != b.shape[1]:
+            raise GLSLError("outerProduct of vectors of different sizes (non-square matrices are not modelled)")
+        return V(f"mat{a.shape[1]}", (b[:, :, None]*a[:, None, :]).astype(F32))
+
+    def b_matrixCompMult(self, x, y): return V(x.t, (x.a*y.a).astype(F32))
+
     def b_isnan(self, x): return V(make_type("bool", vec_info(x.t)[1]), np.isnan(x.a))
     def b_isinf(self, x): return V(make_type("bool", vec_info(x.t)[1]), np.isinf(x.a))
     def b_any(self, x): return V("bool", x.a.any(axis=1))
