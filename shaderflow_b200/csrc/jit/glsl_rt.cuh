@@ -210,7 +210,14 @@ G_DEV mat4 inverse(const mat4& m) {
 }
 
 // .length() of arrays, vectors and matrices
+// GLSL arrays are values: assigned, returned, passed by copy (GLSL 3.30 §4.1.9)
+template <class T, int N> struct arr {
+    T v[N];
+    G_DEV T& operator[](int i) { return v[i]; }
+    G_DEV const T& operator[](int i) const { return v[i]; }
+};
 template <class T, int N> G_DEV int length_of(T (&)[N]) { return N; }
+template <class T, int N> G_DEV int length_of(const arr<T, N>&) { return N; }
 template <class T, int N> G_DEV int length_of(const vec<T, N>&) { return N; }
 template <int C, int R> G_DEV int length_of(const mat<C, R>&) { return C; }
 

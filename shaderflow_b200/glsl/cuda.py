@@ -139,33 +139,39 @@ class Emitter:
                 self.function_returns[(builtin, 2)] = "genType"
 
     # -- types ----------------------------------------------------------------------------------
-    def ctype(self, t) -> str:
+    def ctype(self, t, count: int | None = None) -> str:
+        """GLSL type → C++ type. Arrays are VALUES in GLSL (assigned, returned, passed by copy), so they become
+        g::arr<T, N> (a struct around T[N]) rather than C arrays"""
         if isinstance(t, tuple):
-            raise TranslationError("arrays of arrays / array-typed values are not supported here")
+            _, base, size = t
+            if isinstance(base, tuple):
+                raise TranslationError("arrays of arrays are not supported")
+            if size is None and count is None:
+                raise TranslationError("unsized array without an initialiser")
+            return f"arr<{ident(base)}, {self.expr(size) if size is not None else count}>"
         return ident(t)
 
+    def array_value(self, t, elements) -> str:
+        """An array constructor T[n](e0, e1, …) as a braced g::arr; every element converted like a GLSL constructor argument"""
+        _, base, size = t
+        return self.ctype(t, len(elements)) + "{" + ", ".join(f"{ident(base)}({self.expr(e)})" for e in elements) + "}"
+
     def declarator(self, t, name: str, init=None) -> tuple[str, str]:
-        """→ (C++ declarator 'T name[n]', initialiser text or '')"""
-        dims = []
-        while isinstance(t, tuple):
-            _, t, n = t
-            dims.append(n)
-        text = f"{self.ctype(t)} {ident(name)}"
-        base = self.ctype(t)
-        if not dims:
-            return text, ("" if init is None else f" = {self.expr(init)}")
-        if len(dims) > 1:
+        """→ (C++ declarator 'T name', initialiser text or '')"""
+        if not isinstance(t, tuple):
+            return f"{self.ctype(t)} {ident(name)}", ("" if init is None else f" = {self.expr(init)}")
+        if isinstance(t[1], tuple):
             raise TranslationError(f"'{name}': arrays of arrays are not supported")
-        size = dims[0]
-        if init is not None:
-            if init[0] != "construct" or not isinstance(init[1], tuple):
-                raise TranslationError(f"'{name}': arrays can only be initialised with an array constructor")
-            elements = init[2]
-            count = self.expr(size) if size is not None else str(len(elements))
-            return f"{text}[{count}]", " = {" + ", ".join(f"{base}({self.expr(e)})" for e in elements) + "}"
-        if size is None:
-            raise TranslationError(f"'{name}': unsized array without initialiser")
-        return f"{text}[{self.expr(size)}]", ""
+        if init is None:
+            if t[2] is None:
+                raise TranslationError(f"'{name}': unsized array without initialiser")
+            return f"{self.ctype(t)} {ident(name)}", ""
+        if init[0] == "construct" and isinstance(init[1], tuple):
+            count = len(init[2])
+            return f"{self.ctype(t, count)} {ident(name)}", " = " + self.array_value((t[0], t[1], t[2] if t[2] is not None else init[1][2]), init[2])
+        if t[2] is None:
+            raise TranslationError(f"'{name}': an unsized array needs an array constructor as its initialiser")
+        return f"{self.ctype(t)} {ident(name)}", f" = {self.expr(init)}"          # any array-valued expression (a call, another array)
 
     # -- expressions ----------------------------------------------------------------------------
     def expr(self, e) -> str:
@@ -202,7 +208,7 @@ class Emitter:
         if kind == "construct":
             _, t, args = e
             if isinstance(t, tuple):
-                raise TranslationError("array constructors are only supported as initialisers of array declarations")
+                return self.array_value(t, args)
             return f"{self.ctype(t)}({', '.join(self.expr(a) for a in args)})"
         if kind == "field":
             _, base, name = e
@@ -343,8 +349,7 @@ class Emitter:
             for (ft, fname) in fields:
                 d, _ = self.declarator(ft, fname)
                 self.put(d + ";")
-                if not isinstance(ft, tuple):
-                    plain.append((self.ctype(ft), ident(fname)))
+                plain.append((self.ctype(ft), ident(fname)))
             if len(plain) == len(fields) and fields:
                 self.put(f"G_DEV {ident(sname)}() {{}}")
                 params = ", ".join(f"{t} {n}_" for t, n in plain)
@@ -413,11 +418,7 @@ class Emitter:
             plist = []
             for (direction, pt, pname) in params:
                 pname = pname or f"sfb_unnamed{len(plist)}"
-                if isinstance(pt, tuple):
-                    d, _ = self.declarator(pt, pname)
-                    plist.append(d)
-                else:
-                    plist.append(f"{self.ctype(pt)}{'&' if direction != 'in' else ''} {ident(pname)}")
+                plist.append(f"{self.ctype(pt)}{'&' if direction != 'in' else ''} {ident(pname)}")
             self.put(f"G_DEV {self.ctype(rtype)} {ident(name)}({', '.join(plist)})")
             self.block(body)
         self.put("G_DEV Shader(const RenderParams& P, int i, int j) : ShaderBase(P, i, j) {}")

@@ -17,7 +17,7 @@ from oracle import glsl_np as G
 
 SHADERS = Path(__file__).parent/"shaders"
 CORPUS = ("plasma", "sdf", "bits", "textured", "idioms")
-LATE = ("offsets", "toy", "materials")
+LATE = ("offsets", "toy", "materials", "syntax")
 """Corpus shaders added after the round's GPU budget was spent: held to the evaluator on the host (test_glsl_host.py) and
 compiled by NVRTC (test_glsl_jit.py) like the others; their device run is in tests/test_gpu_zstream.py"""
 W, H = 64, 36
@@ -49,7 +49,8 @@ def stdlib_textures() -> dict:
 
 def evaluate(name: str, Wr: int = W, Hr: int = H):
     """The corpus shader's own text through the mechanical evaluator → (fragColor (Hr, Wr, 4), discarded (Hr, Wr))"""
-    machine = X.Machine(HEADER + (SHADERS/f"{name}.frag").read_text())
+    # gl_FragCoord is a builtin of the fragment stage: declared for the evaluator like any other input
+    machine = X.Machine(HEADER + "in vec4 gl_FragCoord;\n" + (SHADERS/f"{name}.frag").read_text())
     u = uniforms()
     f = G.varyings(u, Wr, Hr)
     n = Wr*Hr
@@ -57,6 +58,8 @@ def evaluate(name: str, Wr: int = W, Hr: int = H):
     for key in VARYINGS:
         inputs[key] = getattr(f, key).reshape(n, 2)
     inputs["fragCoord"] = inputs["stxy"]
+    jj, ii = np.mgrid[0:Hr, 0:Wr]
+    inputs["gl_FragCoord"] = np.stack([ii + 0.5, jj + 0.5, np.full(ii.shape, 0.5), np.ones(ii.shape)], -1).reshape(n, 4).astype(np.float32)
     out = machine.run(n, {k: v for k, v in inputs.items() if k in machine.inputs}, corpus_textures())
     color = np.broadcast_to(out["fragColor"].a, (n, 4)).reshape(Hr, Wr, 4).astype(np.float32)
     gone = machine.discarded

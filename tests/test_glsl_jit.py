@@ -55,9 +55,23 @@ def test_arrays_constants_loops_and_discard():
         const float K[3] = float[](1., 2., 3.);
         float pick(int i) { if (i > 2) discard; return K[i]; }
         void main() { float s = 0; for (int i = 0; i < K.length(); ++i) { s += pick(i); } fragColor = vec4(s); }""")
-    assert "const float K[3] = {float(1.0f), float(2.0f), float(3.0f)};" in t.source
+    assert "const arr<float, 3> K = arr<float, 3>{float(1.0f), float(2.0f), float(3.0f)};" in t.source     # arrays are values
     assert "{ sfb_discarded = true; return float(); }" in t.source
     assert "for (; (i < length_of(K)); (++i))" in t.source
+
+
+def test_arrays_are_values():
+    """Returned, assigned, passed by copy, members of structs (GLSL 3.30 §4.1.9): g::arr<T, N>, not C arrays"""
+    t = glsl.translate("""
+        struct Wave { float amp[3]; vec2 dir; };
+        float[3] weights(float t) { return float[3](t, 1. - t, t*(1. - t)); }
+        float total(float xs[3]) { xs[0] = 0.; return xs[0] + xs[1] + xs[2]; }
+        void main() { float w[3] = weights(astuv.x); float copy[3]; copy = w; Wave wave = Wave(w, gluv);
+                      fragColor = vec4(total(w), w[0], copy[1], wave.amp[2]); }""")
+    assert "G_DEV arr<float, 3> weights(float t)" in t.source and "return arr<float, 3>{float(t)," in t.source
+    assert "G_DEV float total(arr<float, 3> xs)" in t.source                   # by copy: the callee's store stays there
+    assert "arr<float, 3> w = weights(swz<0>(astuv))" in t.source or "arr<float, 3> w = weights(astuv.x)" in t.source
+    assert "arr<float, 3> amp;" in t.source and "G_DEV Wave(arr<float, 3> amp_, vec2 dir_)" in t.source
 
 
 def test_swizzles_as_out_arguments_copy_in_and_back():
