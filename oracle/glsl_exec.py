@@ -1142,6 +1142,9 @@ class Machine:
                 e = self.equal(a.a[k], b.a[k])
                 out = e if out is None else out & e
             return out
+        if a.t in ("mat2", "mat3", "mat4") and a.t == b.t:          # §5.9: equal when every component is
+            e = np.broadcast_arrays(a.a, b.a)[0] == np.broadcast_arrays(a.a, b.a)[1]
+            return e.all(axis=(1, 2))
         ia, ib = vec_info(a.t), vec_info(b.t)
         x, y, _ = self.promote(a, b, ia, ib)
         e = x == y

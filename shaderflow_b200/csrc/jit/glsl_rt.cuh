@@ -62,6 +62,12 @@ template <class T, int N> G_DEV T get(const vec<T, N>& v, int i) { return v.v[i]
     template <class X> G_DEV vec& operator-=(const X& o) { *this = vec(*this - o); return *this; } \
     template <class X> G_DEV vec& operator*=(const X& o) { *this = vec(*this * o); return *this; } \
     template <class X> G_DEV vec& operator/=(const X& o) { *this = vec(*this / o); return *this; } \
+    template <class X> G_DEV vec& operator%=(const X& o) { *this = vec(*this % o); return *this; } \
+    template <class X> G_DEV vec& operator&=(const X& o) { *this = vec(*this & o); return *this; } \
+    template <class X> G_DEV vec& operator|=(const X& o) { *this = vec(*this | o); return *this; } \
+    template <class X> G_DEV vec& operator^=(const X& o) { *this = vec(*this ^ o); return *this; } \
+    template <class X> G_DEV vec& operator<<=(const X& o) { *this = vec(*this << o); return *this; } \
+    template <class X> G_DEV vec& operator>>=(const X& o) { *this = vec(*this >> o); return *this; } \
     G_DEV vec& operator++() { for (int i = 0; i < N; i++) v[i] = v[i] + T(1); return *this; } \
     G_DEV vec& operator--() { for (int i = 0; i < N; i++) v[i] = v[i] - T(1); return *this; } \
     G_DEV vec operator++(int) { vec o = *this; ++*this; return o; } \
