@@ -241,6 +241,13 @@ struct ShaderBase {
         }
     }
 
+    // a square matrix uniform: one slot per column
+    template <int N> G_DEV mat<N, N> sfb_extra_matrix(int slot) const {
+        mat<N, N> m;
+        for (int j = 0; j < N; j++) for (int i = 0; i < N; i++) m.c[j].v[i] = sfb_params->u.extra[slot + j][i];
+        return m;
+    }
+
     G_DEV vec2 agluv2gluv(vec2 p) const { return p*vec2(iAspectRatio, 1); }                                        // :99-100
     G_DEV vec2 gluv2agluv(vec2 p) const { return p/vec2(iAspectRatio, 1); }
     G_DEV vec2 stuv2stxy(vec2 s) const { return g::stuv2stxy(s, iResolution); }                                    // :104

@@ -385,8 +385,18 @@ class Emitter:
                         self.put(f"{self.ctype(t)} {ident(name)} = sfb_extra<{self.ctype(t)}>({len(out.extra)});")
                         out.extra.append(name)
                         out.extra_types.append(t)
+                    elif t in ("mat2", "mat3", "mat4"):
+                        # one slot per column (variable.py's GlslType lists the three square matrices); the value
+                        # arrives as GL takes it: n*n floats, column after column
+                        columns = int(t[3])
+                        if len(out.extra) + columns > MAX_EXTRA:
+                            raise TranslationError(f"more than {MAX_EXTRA} slots of module / user uniforms are read by the shader")
+                        self.put(f"{t} {ident(name)} = sfb_extra_matrix<{columns}>({len(out.extra)});")
+                        for column in range(columns):
+                            out.extra.append(name)
+                            out.extra_types.append(f"{t}:{column}")
                     else:
-                        raise TranslationError(f"uniform '{name}' of type {t} is not supported (scalars, vectors and sampler2D are)")
+                        raise TranslationError(f"uniform '{name}' of type {t} is not supported (scalars, vectors, square matrices and sampler2D are)")
                 elif "in" in quals or "varying" in quals:
                     if name in BASE_VARYINGS:
                         continue

@@ -73,8 +73,19 @@ def pack_uniforms(block: N.Uniforms, values: dict[str, Any], extra_names: list[s
         value = values.get(name)
         if value is None:
             raise RuntimeError(f"Uniform '{name}' required by the shader is not in the scene's pipeline")
-        flat = _scalars(value)
         row = block.extra[slot]
+        if extra_types is not None and extra_types[slot].startswith("mat"):
+            # column `c` of an n x n matrix given as GL takes it (n*n numbers, column after column; nested rows of
+            # columns flatten to the same order)
+            kind, _, column = extra_types[slot].partition(":")
+            n, c = int(kind[3]), int(column or 0)
+            flat = np.asarray(value, dtype=np.float64).ravel()
+            if flat.size != n*n:
+                raise RuntimeError(f"Uniform '{name}' is a {kind}: {n*n} numbers expected, got {flat.size}")
+            for i in range(n):
+                row[i] = float(flat[c*n + i])
+            continue
+        flat = _scalars(value)
         if extra_types is not None and not extra_types[slot].startswith(("float", "vec")):
             bits = np.asarray([int(v) & 0xFFFFFFFF for v in flat[:4]], dtype=np.uint32).view(np.float32)
             C.memmove(row, bits.ctypes.data, bits.nbytes)         # bit patterns: no float conversion (NaN payloads survive)

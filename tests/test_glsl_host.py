@@ -155,3 +155,32 @@ def run_with_camera(tmp_path, text, u, extra, tex):
         return run_on_host(tmp_path, text, J.STDLIB_HEADER, u, extra, tex, J.W, J.H)
     finally:
         N.Uniforms.defaults = original
+
+
+def test_matrix_uniforms_on_the_host(tmp_path):
+    """`Uniform("mat3", name, value)` (variable.py's GlslType): packed one slot per column by pack_uniforms, read back as
+    a matrix by the emitted code; the value travels as GL takes it — n*n numbers, column after column"""
+    text = """
+        uniform mat2 iTwist; uniform mat3 iBasis; uniform mat4 iProj; uniform float iGain;
+        void main() {
+            vec2 p = iTwist*gluv;
+            vec3 q = iBasis*vec3(p, 1.0) + iBasis[2];
+            vec4 h = iProj*vec4(q, 1.0);
+            fragColor = vec4(h.xyz/h.w, iBasis[1][2] + iTwist[0].y + iProj[3][1])*iGain;
+        }"""
+    rng = np.random.default_rng(9)
+    extra = dict(iTwist=rng.uniform(-1, 1, 4), iBasis=rng.uniform(-1, 1, (3, 3)), iProj=np.eye(4).ravel() + rng.uniform(-0.1, 0.1, 16), iGain=0.75)
+    machine = X.Machine(J.HEADER + text)
+    u = J.uniforms()
+    f = G.varyings(u, J.W, J.H)
+    n = J.W*J.H
+    inputs = dict(iTime=np.float32(u.iTime), iFrame=u.iFrame, iResolution=u.iResolution,
+                  **{k: np.asarray(v, np.float32).ravel() if k != "iGain" else np.float32(v) for k, v in extra.items()})
+    for key in J.VARYINGS:
+        inputs[key] = getattr(f, key).reshape(n, 2)
+    out = machine.run(n, {k: v for k, v in inputs.items() if k in machine.inputs}, {})
+    want = np.broadcast_to(out["fragColor"].a, (n, 4)).reshape(J.H, J.W, 4)
+    got, _ = run_on_host(tmp_path, text, J.HEADER, u, extra, {}, J.W, J.H)
+    assert np.abs(got - want).max() <= 2e-6
+    with pytest.raises(RuntimeError, match="9 numbers"):
+        run_on_host(tmp_path, text, J.HEADER, u, dict(extra, iBasis=np.zeros(4)), {}, J.W, J.H)

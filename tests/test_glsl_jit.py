@@ -102,8 +102,15 @@ def test_translation_errors_are_reported():
     many = "".join(f"uniform float u{i};" for i in range(17))
     with pytest.raises(glsl.TranslationError, match="more than 16"):
         glsl.translate("void main() { fragColor = vec4(" + "+".join(f"u{i}" for i in range(17)) + "); }", many)
-    with pytest.raises(glsl.TranslationError, match="mat3"):
-        glsl.translate("uniform mat3 m; void main() { fragColor = vec4(m[0], 1); }")
+    with pytest.raises(glsl.TranslationError, match="mat3x2"):
+        glsl.translate("uniform mat3x2 m; void main() { fragColor = vec4(m[0], 1, 1); }")
+    # square matrices take one slot per column (variable.py's GlslType: mat2, mat3, mat4)
+    t = glsl.translate("uniform float a; uniform mat3 m; uniform mat2 k; void main() { fragColor = vec4(m[0]*a, k[1].x); }")
+    assert t.extra == ["a", "m", "m", "m", "k", "k"] and t.extra_types == ["float", "mat3:0", "mat3:1", "mat3:2", "mat2:0", "mat2:1"]
+    assert "mat3 m = sfb_extra_matrix<3>(1);" in t.source and "mat2 k = sfb_extra_matrix<2>(4);" in t.source
+    five = "".join(f"uniform mat4 m{i};" for i in range(5))
+    with pytest.raises(glsl.TranslationError, match="more than 16"):
+        glsl.translate("void main() { fragColor = " + "+".join(f"m{i}[0]" for i in range(5)) + "; }", five)
 
 
 def test_float_literals_carry_the_float32_value():
@@ -162,3 +169,10 @@ def test_the_references_own_assembled_programs_translate_and_compile():
     assert len(done) == 2*len(REFERENCE_SCENES) + 2 and all(ok for ok, _, _ in done.values()), done     # + MultiShader.child, Life.iLife
     assert done["Visualizer.iScreen"][1:] == [["iAudioVolume", "iAudioSTD"], ["iWaveform0x0", "iSpectrogram0x0", "background0x0"]]
     assert done["Life.iLife"][1:] == [["iLifePeriod", "iLifeSize"], ["iLife1x0"]]
+
+
+@needs_nvrtc
+def test_matrix_uniforms_compile_to_sass():
+    image, translation, log = glsl.build("""uniform mat2 iTwist; uniform mat3 iBasis; uniform mat4 iProj;
+        void main() { vec4 h = iProj*vec4(iBasis*vec3(iTwist*gluv, 1.0), 1.0); fragColor = h/h.w; }""", J.HEADER)
+    assert image[:4] == b"\x7fELF" and translation.extra == ["iTwist"]*2 + ["iBasis"]*3 + ["iProj"]*4 and "error" not in log.lower()
