@@ -9,8 +9,8 @@ texture uploads (module.py:202-277) — replaced by the GPU producer of csrc/pia
   per frame         sfb_piano_roll      the (128 x 256) roll texture straight into the texture's storage;
                     the keys / channel textures sample row k of the tracks (zero-copy bind)
 
-Out of scope here: FluidSynth playback (module.py:289-328; realtime only) and MIDI file parsing
-(`load_midi` needs the third-party pretty_midi, module.py:171-199) — notes are added with `add_note`.
+Out of scope here: FluidSynth playback (module.py:289-328; realtime only). `load_midi` (module.py:166-196) reads
+Standard MIDI Files natively (piano/midi.py) instead of through the third-party pretty_midi.
 """
 from __future__ import annotations
 
@@ -163,9 +163,23 @@ class ShaderPiano(ShaderModule):
         self._invalidate()
 
     def load_midi(self, path: Path):
-        raise RuntimeError(logger.error(
-            "ShaderPiano.load_midi needs the third-party pretty_midi parser (reference piano/module.py:171-199), "
-            "which this backend does not bundle: add the notes with add_note(PianoNote(...))"))
+        """module.py:166-196 without pretty_midi: piano/midi.py restates what it (and mido underneath) do. Notes are
+        added instrument by instrument, the channel being the instrument's index; tempo changes fill the tempo
+        texture, row k = (seconds, BPM)"""
+        if not (path := Path(path)).exists():
+            logger.warn(f"Input Midi file not found ({path})")
+            return
+        from shaderflow_b200.piano.midi import read_midi
+        instruments, tempo = read_midi(path)
+        for channel, instrument in enumerate(instruments):
+            for (pitch, start, end, velocity) in instrument.notes:
+                self.add_note(PianoNote(note=pitch, start=start, end=end, channel=channel, velocity=velocity))
+        for when, bpm in tempo:
+            self.tempo.append((when, bpm))
+        rows = np.zeros((100, 1, 2), np.float32)
+        for offset, (when, bpm) in enumerate(list(self.tempo)[:100]):
+            rows[offset, 0] = (when, bpm)
+        self.tempo_texture.write(rows)
 
     # -- GPU producer --------------------------------------------------------------------------------
     def _upload(self) -> None:
