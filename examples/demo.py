@@ -198,12 +198,15 @@ class PianoRoll(ShaderScene):
     module but neither a scene nor a fragment for it). Notes come from `notes` rows (pitch, start, end, channel,
     velocity) or a seeded synthetic list: 4 channels, 16 notes/s, pitches 36-96, 0.1-1 s."""
     notes = None
+    midi = None         # path of a Standard MIDI File: its notes instead of `notes` / the synthetic list
     seconds: float = 10.0
 
     def build(self):
         from shaderflow.piano import PianoNote, ShaderPiano
         self.piano = ShaderPiano(scene=self)
-        for (pitch, start, end, channel, velocity) in (self.notes if self.notes is not None else synthetic_notes(self.seconds)):
+        if self.midi is not None:
+            self.piano.load_midi(self.midi)
+        for (pitch, start, end, channel, velocity) in (() if self.midi is not None else self.notes if self.notes is not None else synthetic_notes(self.seconds)):
             self.piano.add_note(PianoNote(note=int(pitch), start=float(start), end=float(end), channel=int(channel), velocity=int(velocity)))
         self.shader.fragment = (shaders/"piano.frag")
 
