@@ -53,5 +53,4 @@ def test_piano_module_api_without_gpu():
     assert piano.roll_texture.size == (256, 128) and piano.keys_texture.size == (128, 1)
     piano.normalize_velocities(minimum=40, maximum=100)
     assert {n.velocity for n in piano.notes} == {70}                     # the reference's dropped interpolation (module.py:163-166)
-    with pytest.raises(RuntimeError, match="pretty_midi"):
-        piano.load_midi("song.mid")
+    piano.load_midi("no_such_song.mid")                                   # warns and returns, like the reference (tests/test_midi.py reads real files)
