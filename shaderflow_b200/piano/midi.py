@@ -139,7 +139,10 @@ def tick_to_time(scales: list[tuple[int, float]], max_tick: int) -> np.ndarray:
 
 def read_midi(path) -> tuple[list[Instrument], list[tuple[float, float]]]:
     """→ (instruments in pretty_midi's order, tempo changes as (seconds, BPM))"""
-    resolution, tracks = read_events(Path(path).read_bytes())
+    try:
+        resolution, tracks = read_events(Path(path).read_bytes())
+    except IndexError:
+        raise ValueError(f"'{path}': the MIDI file ends inside an event") from None
     scales = tick_scales(tracks, resolution)
     max_tick = max((event.tick for track in tracks for event in track), default=0) + 1
     if max_tick > MAX_TICK:

@@ -64,6 +64,9 @@ def test_tempo_map_is_track_zeros_and_accumulates_like_pretty_midi(tmp_path):
     scale = [60.0/(bpm*480) for bpm in (120.0, 240.0, 60.0)]
     assert (pitch, velocity) == (60, 90) and start == 100*scale[0]
     assert end == (480*scale[0] + 480*scale[1]) + scale[2]*(1920 - 960)
+    (tmp_path/"cut.mid").write_bytes(smf(480, [conductor, other])[:-6])
+    with pytest.raises(ValueError, match="ends inside"):
+        M.read_midi(tmp_path/"cut.mid")
     # no set_tempo at all: 120 BPM
     (tmp_path/"plain.mid").write_bytes(smf(96, [track([(0, on(3, 40, 1)), (96, off(3, 40))])], fmt=0))
     instruments, changes = M.read_midi(tmp_path/"plain.mid")
