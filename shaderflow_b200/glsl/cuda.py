@@ -254,6 +254,16 @@ class Emitter:
         prefix = "const " if "const" in quals else ""
         for (t, name, init) in decls:
             d, i = self.declarator(t, name, init)
+            if init is not None:
+                mentioned: set = set()
+                names_used(init, mentioned)
+                if name in mentioned:
+                    # `vec2 gluv = gluv - offset;` (camera.glsl:101): in GLSL a name is not in scope in its own initialiser,
+                    # so this reads the OUTER gluv; in C++ it would read the new, uninitialised one
+                    self.shadows = getattr(self, "shadows", 0) + 1
+                    held = f"sfb_outer{self.shadows}"
+                    self.put(f"const auto {held}{i};")
+                    i = f" = {held}"
             self.put(f"{prefix}{d}{i};")
 
     def block(self, node) -> None:

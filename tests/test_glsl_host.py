@@ -54,7 +54,8 @@ int main(int argc, char** argv) {
 '''
 
 
-def run_on_host(tmp_path, fragment: str, header: str, uniforms: G.Uniforms, extra: dict, textures: dict, Wr: int, Hr: int):
+def run_on_host(tmp_path, fragment: str, header: str, uniforms: G.Uniforms, extra: dict, textures: dict, Wr: int, Hr: int, block=None):
+    """`block`: callable(translation) → a packed N.Uniforms, for callers that set more than time / frame / extras"""
     translation = glsl.translate(fragment, header)
     source = ('#include "host_shim.h"\n#include "sfb200.h"\n#include "render_params.h"\n#include "glsl_rt.cuh"\n#include "shaderflow_rt.cuh"\n'
               + translation.source + MAIN)
@@ -63,10 +64,13 @@ def run_on_host(tmp_path, fragment: str, header: str, uniforms: G.Uniforms, extr
                             "-I", str(ROOT/"shaderflow_b200"/"csrc"), "-I", str(ROOT/"shaderflow_b200"/"csrc"/"jit"),
                             str(tmp_path/"program.cpp"), "-o", str(tmp_path/"program")], capture_output=True, text=True)
     assert build.returncode == 0, build.stderr[-3000:]
-    W, H = uniforms.iResolution
-    block = N.Uniforms.defaults(W, H)
-    block.iTime, block.iTau, block.iFrame = float(uniforms.iTime), float(uniforms.iTau), int(uniforms.iFrame)
-    pack_uniforms(block, {name: extra[name] for name in translation.extra}, translation.extra, translation.extra_types)
+    if block is not None:
+        block = block(translation)
+    else:
+        W, H = uniforms.iResolution
+        block = N.Uniforms.defaults(W, H)
+        block.iTime, block.iTau, block.iFrame = float(uniforms.iTime), float(uniforms.iTau), int(uniforms.iFrame)
+        pack_uniforms(block, {name: extra[name] for name in translation.extra}, translation.extra, translation.extra_types)
     (tmp_path/"uniforms.bin").write_bytes(bytes(block))
     args = []
     for k, name in enumerate(translation.samplers):

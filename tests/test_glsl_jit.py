@@ -74,6 +74,14 @@ def test_arrays_are_values():
     assert "arr<float, 3> amp;" in t.source and "G_DEV Wave(arr<float, 3> amp_, vec2 dir_)" in t.source
 
 
+def test_a_name_is_not_in_scope_in_its_own_initialiser():
+    """camera.glsl:101 `vec2 gluv = gluv - ...;` inside a function reads the GLOBAL gluv (GLSL 3.30 §4.2.2); C++ would
+    read the new variable — found by running the reference's stereoscopic camera through the translator"""
+    t = glsl.translate("void main() { float x = 2.0; { float x = x*3.0; vec2 gluv = gluv - x; fragColor = vec4(gluv, x, 1.0); } }")
+    assert "const auto sfb_outer1 = (x * 3.0f);" in t.source and "float x = sfb_outer1;" in t.source
+    assert "vec2 gluv = sfb_outer2;" in t.source
+
+
 def test_swizzles_as_out_arguments_copy_in_and_back():
     """`rotate(p.xz, a)` with an inout parameter: a swizzle is not an lvalue in C++, so the call copies in, calls, copies back"""
     text = """

@@ -1,0 +1,91 @@
+"""The REFERENCE's own shader text through this backend's run-time path, without a GPU (build container only).
+
+For the cases of oracle/glsl_cases.py the text the reference assembles and hands to the GL driver (its header, its whole
+GLSL std-lib, camera.glsl, the example's fragment — captured by oracle/ref_scene.py from the reference's unmodified
+Python) is translated by shaderflow_b200/glsl, the emitted C++ is compiled for the host over tests/host_shim.h
+(tests/test_glsl_host.py's harness), run on the case's inputs and held to the committed golden of that case —
+tests/golden/glsl_<case>.npz, the same text executed by the mechanical evaluator. So: reference text in, the
+reference's pixels out, through the translator and the run-time headers the GPU build uses."""
+import json
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import glsl_cases as C
+from tests.helpers import native_uniforms
+from tests.test_glsl_host import run_on_host
+
+ROOT = Path(__file__).resolve().parents[1]
+REFERENCE = Path("/root/reference")
+pytestmark = [pytest.mark.reference, pytest.mark.timeout(900),
+              pytest.mark.skipif(not REFERENCE.exists() or shutil.which("g++") is None, reason="needs /root/reference and g++")]
+
+# continuous shaders are held everywhere; the escape-time fractals flip whole fragments on an ulp
+CASES = ["default", "default_stereo", "default_equirect", "default_rotated", "shadertoy", "visualizer", "visualizer_rotated",
+         "mandelbrot", "tetration", "raymarch", "bars", "waveform", "dynamics", "audio", "multishader_child", "multishader",
+         "multipass_layer1", "life_visuals"]
+DISCONTINUOUS = {"mandelbrot", "tetration", "raymarch", "life_visuals", "bars", "waveform", "visualizer", "visualizer_rotated"}
+
+_CAPTURE = """
+import json, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from oracle import glsl_np as G, ref_scene
+out = {}
+for scene in sys.argv[2:]:
+    cap = ref_scene.capture(scene, background=G.synthetic_background(16, 9))
+    out[scene] = {name: program["fragment"] for name, program in cap["programs"].items()}
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.fixture(scope="module")
+def reference_text():
+    """scene → program → assembled fragment text, captured in a child process (importing the reference rebinds `shaderflow`)"""
+    cases = {c.name: c for c in C.small_cases()}
+    scenes = sorted({cases[name].ref_scene for name in CASES})
+    run = subprocess.run([sys.executable, "-c", _CAPTURE, str(ROOT), *scenes], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-3000:]
+    return json.loads(next(line for line in run.stdout.splitlines() if line.startswith("RESULT "))[7:])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reference_text_through_the_translator_reproduces_its_golden(tmp_path, golden_dir, reference_text, name):
+    case = {c.name: c for c in C.small_cases()}[name]
+    gold = np.load(golden_dir/f"glsl_{name}.npz")
+    text = reference_text[case.ref_scene][case.program]
+    from oracle import glsl_exec as X
+    assert X.text_digest(text) == str(gold["fragment_sha1"]), "the reference's text is not the one the golden was made from"
+    textures = C.exec_samplers(case.tex)
+
+    def block(translation):
+        info = dict(extra=translation.extra, extra_types=translation.extra_types, samplers=translation.samplers)
+        return native_uniforms(case.uniforms, info) if not set(translation.extra) - set(case.uniforms.extra) else \
+            native_uniforms(_with_defaults(case.uniforms, translation.extra), info)
+    got, _ = run_on_host(tmp_path, text, "", case.uniforms, {}, textures, case.Wr, case.Hr, block=block)
+    want = gold["screen_f32"]
+    if case.rows is not None:
+        got = got[case.rows]
+    err = np.abs(got - want)/np.maximum(1.0, np.abs(want))          # colours before the store are not bounded by 1
+    if name in DISCONTINUOUS:
+        assert (err <= 1e-4).mean() >= 0.995, (name, (err <= 1e-4).mean(), err.max())
+    else:
+        assert err.max() <= 1e-4, (name, err.max())
+    assert np.median(err) <= 1e-6
+
+
+def _with_defaults(u, names):
+    """Uniforms the assembled text reads but the case leaves at the scene's defaults"""
+    import dataclasses
+    known = C.exec_uniforms(u)
+    extra = dict(u.extra)
+    for name in names:
+        if name not in extra:
+            if name not in known:
+                raise KeyError(f"the case has no value for uniform {name}")
+            extra[name] = known[name]
+    return dataclasses.replace(u, extra=extra)
