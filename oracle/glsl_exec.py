@@ -543,10 +543,9 @@ class Parser:
         if k == "float":
             return ("lit", "float", float(v.rstrip("fF")))
         if k == "int":
-            if v[-1] in "uU":
-                return ("lit", "uint", int(v[:-1], 0))
-            return ("lit", "int", int(v, 0) if v.lower().startswith("0x") or v == "0" or not v.startswith("0")
-                    else int(v, 8))
+            digits = v.rstrip("uU")
+            value = int(digits, 0) if digits.lower().startswith("0x") or digits == "0" or not digits.startswith("0") else int(digits, 8)
+            return ("lit", "uint" if v[-1] in "uU" else "int", value)
         if v == "(":
             e = self.expr(); self.expect(")")
             return e

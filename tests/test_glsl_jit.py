@@ -74,6 +74,26 @@ def test_arrays_are_values():
     assert "arr<float, 3> amp;" in t.source and "G_DEV Wave(arr<float, 3> amp_, vec2 dir_)" in t.source
 
 
+def test_small_print_of_the_grammar():
+    """#version / #extension / #pragma / #line, layout() and invariant qualifiers, octal and suffixed literals, C++ keywords
+    as GLSL names, functions used before their definition, non-square matrices"""
+    t = glsl.translate("""#version 330
+        #extension GL_ARB_gpu_shader5 : enable
+        #pragma optimize(on)
+        invariant gl_Position;
+        layout(location = 0) out vec4 color;
+        float f(float this, float new) { float class = this + new; return later(class); }
+        void main() {
+        #line 20 1
+            uint a = 0xFFu, b = 017u; int d = 010;
+            mat2x3 m = mat2x3(1, 2, 3, 4, 5, 6);
+            color = vec4(m*gluv, f(float(a + b), float(d)));
+        }
+        float later(float x) { return x*x; }""", J.HEADER.replace("out vec4 fragColor; ", ""))
+    assert "uint a = 255u;" in t.source and "b = 15u;" in t.source and "int d = 8;" in t.source
+    assert "vec4& color = fragColor;" in t.source and "mat2x3 m = mat2x3(1, 2, 3, 4, 5, 6);" in t.source
+
+
 def test_a_name_is_not_in_scope_in_its_own_initialiser():
     """camera.glsl:101 `vec2 gluv = gluv - ...;` inside a function reads the GLOBAL gluv (GLSL 3.30 §4.2.2); C++ would
     read the new variable — found by running the reference's stereoscopic camera through the translator"""
