@@ -17,7 +17,7 @@ from oracle import glsl_np as G
 
 SHADERS = Path(__file__).parent/"shaders"
 CORPUS = ("plasma", "sdf", "bits", "textured", "idioms")
-LATE = ("offsets", "toy", "materials", "syntax", "integers", "conversions")
+LATE = ("offsets", "toy", "materials", "syntax", "integers", "conversions", "semantics")
 """Corpus shaders added after the round's GPU budget was spent: held to the evaluator on the host (test_glsl_host.py) and
 compiled by NVRTC (test_glsl_jit.py) like the others; their device run is in tests/test_gpu_zstream.py"""
 W, H = 64, 36
