@@ -398,9 +398,12 @@ G_DEV vec4 texture(sampler2D t, vec2 uv) {
 template <class S> G_DEV vec4 texture(sampler2D t, vec2 uv, S) { return texture(t, uv); }           // bias: one mip level
 template <class S> G_DEV vec4 textureLod(sampler2D t, vec2 uv, S) { return texture(t, uv); }
 template <class S> G_DEV ivec2 textureSize(sampler2D t, S) { return ivec2(t.s->w, t.s->h); }
+// a fetch outside the image is undefined in GLSL 3.30; zeros here — what robust buffer access (and the GL drivers at
+// hand) return, and the rule the ahead-of-time kernels and the checker follow (scenes.cuh texel_fetch_r, Life's borders)
 template <class S> G_DEV vec4 texelFetch(sampler2D t, ivec2 p, S) {
     const DevSampler& s = *t.s;
-    return texel_at(s, ::min(::max(p.x, 0), s.w - 1), ::min(::max(p.y, 0), s.h - 1));
+    if (p.x < 0 || p.y < 0 || p.x >= s.w || p.y >= s.h) return vec4(0.0f);
+    return texel_at(s, p.x, p.y);
 }
 // the offset / projective / explicit-gradient forms (GLSL 3.30 §8.7). Textures here have one level, so a gradient only
 // ever selects that level; an offset is a whole number of texels added to the texel coordinates before wrapping

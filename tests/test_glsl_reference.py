@@ -27,8 +27,12 @@ pytestmark = [pytest.mark.reference, pytest.mark.timeout(900),
 # continuous shaders are held everywhere; the escape-time fractals flip whole fragments on an ulp
 CASES = ["default", "default_stereo", "default_equirect", "default_rotated", "shadertoy", "visualizer", "visualizer_rotated",
          "mandelbrot", "tetration", "raymarch", "bars", "waveform", "dynamics", "audio", "multishader_child", "multishader",
-         "multipass_layer1", "life_visuals"]
-DISCONTINUOUS = {"mandelbrot", "tetration", "raymarch", "life_visuals", "bars", "waveform", "visualizer", "visualizer_rotated"}
+         "multipass_layer1", "life_visuals", "visualizer_quiet", "visualizer_native", "visualizer_pillarbox", "raymarch_rotated",
+         "multipass_layer0", "life_simulation_f6", "life_simulation_f7"]
+# not here: motionblur reads 60 samplers (10 frames x 2 layers x 3 names), past the 20 slots of a run-time compiled program —
+# its ahead-of-time kernel serves it (tests/test_gpu_golden.py)
+DISCONTINUOUS = {"mandelbrot", "tetration", "raymarch", "raymarch_rotated", "life_visuals", "bars", "waveform", "visualizer",
+                 "visualizer_rotated", "visualizer_quiet", "visualizer_native", "visualizer_pillarbox", "life_simulation_f6", "life_simulation_f7"}
 
 _CAPTURE = """
 import json, sys
@@ -62,6 +66,13 @@ def test_reference_text_through_the_translator_reproduces_its_golden(tmp_path, g
     assert X.text_digest(text) == str(gold["fragment_sha1"]), "the reference's text is not the one the golden was made from"
     textures = C.exec_samplers(case.tex)
 
+    class WithBlanks(dict):
+        """A sampler the text names but this layer never reads (multipass layer 0 and its own previous output)"""
+        def __missing__(self, key):
+            from oracle import glsl_np as G
+            return G.Texture(np.zeros((2, 2, 4), np.uint8))
+    textures = WithBlanks(textures)
+
     def block(translation):
         info = dict(extra=translation.extra, extra_types=translation.extra_types, samplers=translation.samplers)
         return native_uniforms(case.uniforms, info) if not set(translation.extra) - set(case.uniforms.extra) else \
@@ -89,3 +100,28 @@ def _with_defaults(u, names):
                 raise KeyError(f"the case has no value for uniform {name}")
             extra[name] = known[name]
     return dataclasses.replace(u, extra=extra)
+
+
+def test_final_glsl_through_the_translator(tmp_path, golden_dir, reference_text):
+    """fragment/final.glsl (the SSAA resolve every export ends with) as the reference assembles it, over the (ssaa,
+    subsample) geometries of the golden — incl. the reference's default (1, 2)"""
+    from oracle import glsl_np as G
+    gold = np.load(golden_dir/"glsl_final.npz")
+    text = reference_text["Basic"]["iFinal"]
+    W, H = 40, 24
+    for k, (ssaa, subsample) in enumerate(C.FINAL_GEOMETRIES):
+        screen = G.Texture(C.final_screen(W, H, ssaa), linear=True, repeat_x=False, repeat_y=False)
+        u = G.Uniforms(iResolution=(W, H), iWantAspect=W/H, iSSAA=float(ssaa), extra=dict(iSubsample=subsample))
+
+        def block(translation):
+            info = dict(extra=translation.extra, extra_types=translation.extra_types, samplers=translation.samplers)
+            packed = native_uniforms(u, info)
+            if hasattr(packed, "iSubsample"):
+                packed.iSubsample = subsample
+            return packed
+        work = tmp_path/f"g{k}"
+        work.mkdir()
+        got, _ = run_on_host(work, text, "", u, {}, {"iScreen0x0": screen}, W, H, block=block)
+        want = gold[f"s{ssaa}_k{subsample}_f32"]
+        assert np.abs(got[..., :3] - want).max() <= 2e-6, (ssaa, subsample, np.abs(got[..., :3] - want).max())
+        assert np.all(got[..., 3] == 1.0)
