@@ -59,11 +59,12 @@ def run_on_host(tmp_path, fragment: str, header: str, uniforms: G.Uniforms, extr
     translation = glsl.translate(fragment, header)
     source = ('#include "host_shim.h"\n#include "sfb200.h"\n#include "render_params.h"\n#include "glsl_rt.cuh"\n#include "shaderflow_rt.cuh"\n'
               + translation.source + MAIN)
-    (tmp_path/"program.cpp").write_text(source)
-    build = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-I", str(ROOT/"tests"), "-I", str(ROOT/"include"),
-                            "-I", str(ROOT/"shaderflow_b200"/"csrc"), "-I", str(ROOT/"shaderflow_b200"/"csrc"/"jit"),
-                            str(tmp_path/"program.cpp"), "-o", str(tmp_path/"program")], capture_output=True, text=True)
-    assert build.returncode == 0, build.stderr[-3000:]
+    if not ((tmp_path/"program").exists() and (tmp_path/"program.cpp").exists() and (tmp_path/"program.cpp").read_text() == source):
+        (tmp_path/"program.cpp").write_text(source)                # (same text in the same directory: the binary is reused)
+        build = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-I", str(ROOT/"tests"), "-I", str(ROOT/"include"),
+                                "-I", str(ROOT/"shaderflow_b200"/"csrc"), "-I", str(ROOT/"shaderflow_b200"/"csrc"/"jit"),
+                                str(tmp_path/"program.cpp"), "-o", str(tmp_path/"program")], capture_output=True, text=True)
+        assert build.returncode == 0, build.stderr[-3000:]
     if block is not None:
         block = block(translation)
     else:

@@ -125,3 +125,74 @@ def test_final_glsl_through_the_translator(tmp_path, golden_dir, reference_text)
         want = gold[f"s{ssaa}_k{subsample}_f32"]
         assert np.abs(got[..., :3] - want).max() <= 2e-6, (ssaa, subsample, np.abs(got[..., :3] - want).max())
         assert np.all(got[..., 3] == 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The CUDA std-lib (csrc/jit/shaderflow_rt.cuh) against the reference's GLSL std-lib, function by function
+
+_ARGUMENT = {
+    "float": "(gluv.x*1.3 + 0.37*float({k} + 1))", "int": "(int(stxy.x) % 5 + {k})", "bool": "(gluv.x > 0.1*float({k}))",
+    "vec2": "(gluv*1.1 + vec2(0.2, -0.1)*float({k} + 1))", "vec3": "(vec3(gluv, astuv.x)*1.2 + 0.1*float({k}))",
+    "vec4": "(vec4(gluv, astuv)*0.9 + 0.05*float({k}))", "mat2": "mat2(gluv, astuv + 0.1*float({k}))", "sampler2D": "background",
+}
+_RESULT = {"float": "vec4({r})", "int": "vec4(float({r}))", "bool": "vec4(float({r}))", "vec2": "vec4({r}, 0.0, 1.0)",
+           "vec3": "vec4({r}, 1.0)", "vec4": "{r}", "mat2": "vec4(({r})[0], ({r})[1])"}
+
+
+def _probe_shader(functions) -> str:
+    cases = []
+    for index, (rtype, name, params) in enumerate(functions):
+        before, args = [], []
+        for k, (direction, ptype) in enumerate(params):
+            value = _ARGUMENT[ptype].format(k=k)
+            if direction == "in":
+                args.append(value)
+            else:
+                before.append(f"{ptype} held{k} = {value};")
+                args.append(f"held{k}")
+        call = f"{name}({', '.join(args)})"
+        cases.append(f"        case {index}: {{ {' '.join(before)} fragColor = {_RESULT[rtype].format(r=call)}; break; }}")
+    return "uniform int iProbe;\nvoid main() {\n    fragColor = vec4(0.0);\n    switch (iProbe) {\n" + "\n".join(cases) + "\n    }\n}\n"
+
+
+def test_cuda_std_lib_equals_the_references_glsl_function_by_function(tmp_path, reference_text):
+    """Every function of resources/shaders/include/shaderflow.glsl (86 with overloads) called with the same arguments
+    twice: once with the reference's GLSL definition in front of the call (a user definition hides the CUDA std-lib
+    entry of the same name), once without (the hand-written CUDA std-lib of csrc/jit/shaderflow_rt.cuh answers). Both go
+    through the translator and run on the host; the two images must agree"""
+    from oracle import glsl_np as G
+    from shaderflow_b200.glsl import frontend
+    from tests import jit_cases as J
+    library = (REFERENCE/"shaderflow"/"resources"/"shaders"/"include"/"shaderflow.glsl").read_text()
+    items, _ = frontend.parse(library, None, types=("Camera",))
+    functions = [(i[1], i[2], [(d, t) for d, t, _ in i[3]]) for i in items if i[0] == "function"]
+    assert len(functions) >= 80 and all(r in _RESULT and all(t in _ARGUMENT for _, t in p) for r, _, p in functions)
+    probe = _probe_shader(functions)
+    assembled = reference_text["Dynamics"]["iScreen"]                       # header + the whole std-lib + camera + the example
+    theirs = assembled[:assembled.rindex("void main()")] + probe
+    ours = probe
+    background = {"background0x0": J.stdlib_textures()["background"]}
+    # the comparison means something only if the two sides take their definitions from different places
+    import re
+    from shaderflow_b200 import glsl
+    emitted = lambda text, header: set(re.findall(r"G_DEV [\w<>, :]+ (\w+)\(", glsl.translate(text, header).source))
+    assert len(emitted(theirs, "")) >= 60 and emitted(ours, J.STDLIB_HEADER) == {"main"}
+    worst = {}
+    for index, (rtype, name, params) in enumerate(functions):
+        u = J.uniforms(extra=dict(iProbe=index, iShaderDynamics=0.42))
+
+        def block(translation):
+            info = dict(extra=translation.extra, extra_types=translation.extra_types, samplers=translation.samplers)
+            return native_uniforms(u, info)
+        images = []
+        for label, text, header in (("theirs", theirs, ""), ("ours", ours, J.STDLIB_HEADER)):
+            work = tmp_path/label
+            work.mkdir(exist_ok=True)
+            image, _ = run_on_host(work, text, header, u, {}, background, 32, 18, block=block)
+            images.append(image)
+        a, b = images
+        assert np.array_equal(np.isnan(a), np.isnan(b)), (index, name)
+        error = np.nan_to_num(np.abs(a - b)/np.maximum(1.0, np.abs(a)), nan=0.0, posinf=0.0)
+        worst[f"{name}/{len(params)}"] = max(worst.get(f"{name}/{len(params)}", 0.0), float(error.max()))
+    bad = {k: v for k, v in worst.items() if v > 1e-5}
+    assert not bad, bad
