@@ -196,3 +196,44 @@ def test_cuda_std_lib_equals_the_references_glsl_function_by_function(tmp_path, 
         worst[f"{name}/{len(params)}"] = max(worst.get(f"{name}/{len(params)}", 0.0), float(error.max()))
     bad = {k: v for k, v in worst.items() if v > 1e-5}
     assert not bad, bad
+
+
+def test_cuda_camera_equals_the_references_camera_glsl(tmp_path, reference_text):
+    """GetCamera(iCamera) under eight camera set-ups — the three projections, 2D / 3D modes, displaced, zoomed, isometric,
+    rotated — once through the reference's camera.glsl, once through sfb_get_camera of csrc/jit/shaderflow_rt.cuh: every
+    field of the Camera a fragment can read agrees"""
+    from tests import jit_cases as J
+    probe = """uniform int iProbe;
+void main() {
+    GetCamera(iCamera);       // the reference's macro pastes name##Mode, name##Position, …: the camera is named after its uniforms
+    if (iProbe == 0) fragColor = vec4(iCamera.gluv, iCamera.stuv);
+    if (iProbe == 1) fragColor = vec4(iCamera.agluv, iCamera.astuv);
+    if (iProbe == 2) fragColor = vec4(iCamera.glxy, iCamera.stxy);
+    if (iProbe == 3) fragColor = vec4(iCamera.origin, float(iCamera.out_of_bounds));
+    if (iProbe == 4) fragColor = vec4(iCamera.target, float(iCamera.mode) + 0.1*float(iCamera.projection));
+    if (iProbe == 5) fragColor = vec4(iCamera.position, iCamera.zoom) + vec4(iCamera.forward, iCamera.isometric) + 2.0*vec4(iCamera.right, iCamera.focal_length);
+    if (iProbe == 6) fragColor = vec4(iCamera.up + 3.0*iCamera.zenith, iCamera.separation) + vec4(iCamera.backward + iCamera.left - iCamera.down, iCamera.orbital + 2.0*iCamera.dolly);
+    if (iProbe == 7) fragColor = vec4(iCamera.plane_point, 1.0) + vec4(iCamera.plane_normal, 0.0);
+}
+"""
+    assembled = reference_text["Dynamics"]["iScreen"]
+    theirs = assembled[:assembled.rindex("void main()")] + probe
+    rotated = C.rotated_camera() if hasattr(C, "rotated_camera") else {}
+    cameras = list(J.STDLIB_CAMERAS) + [dict(iCameraMode=0), dict(iCameraMode=2, iCameraProjection=0, iCameraPosition=(0.3, 0.2, -1.0)),
+                                        dict(iCameraProjection=1, iCameraSeparation=0.2, iCameraZoom=0.6), rotated]
+    for c, camera in enumerate(cameras):
+        for index in range(8):
+            u = J.uniforms(extra=dict(iProbe=index, iShaderDynamics=0.42), **camera)
+
+            def block(translation):
+                info = dict(extra=translation.extra, extra_types=translation.extra_types, samplers=translation.samplers)
+                return native_uniforms(u, info)
+            images = []
+            for label, text, header in (("theirs", theirs, ""), ("ours", probe, "")):
+                work = tmp_path/label
+                work.mkdir(exist_ok=True)
+                images.append(run_on_host(work, text, header, u, {}, {}, 32, 18, block=block)[0])
+            a, b = images
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (c, index)
+            error = np.nan_to_num(np.abs(a - b)/np.maximum(1.0, np.abs(a)), nan=0.0, posinf=0.0)
+            assert error.max() <= 1e-5, (c, camera, index, float(error.max()))
