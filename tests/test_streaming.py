@@ -194,3 +194,27 @@ def test_frames_of_other_ranks_are_recorded_but_not_computed(no_device):
         assert np.array_equal(s["wave"], want["wave"][k])
     assert [c[1] for c in fake.calls if c[0] == "stft"] == [1]*frames       # length 1 texture: transformed, not scanned
     assert [c[1] for c in fake.calls if c[0] == "track" and c[2]] == [9, 10, 11, 12]
+
+
+@pytest.mark.parametrize("fps,seconds_of_audio,seconds", [(24.0, 0.3, 0.5), (60.0, 0.5, 0.4)])
+def test_streamed_export_at_the_device_tests_settings(no_device, fps, seconds_of_audio, seconds):
+    """The two set-ups tests/test_gpu_zstream.py exports on the device — a non-integer hop (44100/24) with the audio
+    ending before the export does, and 60 fps — here against the stand-in context: the chunks come from the library's own
+    frame clock (sfb_frame_clock, host code), and every frame publishes the oracle's whole-clip state"""
+    from shaderflow_b200 import _native as N, synthetic
+    clip = synthetic.noise(seconds_of_audio)
+    frames = round(seconds*fps)
+    _, dt, tell = N.frame_clock(frames, fps, 1.0, 44100, 2, clip.shape[1])
+    assert tell[-1] == clip.shape[1] if seconds_of_audio < seconds else tell[-1] < clip.shape[1]
+    cfg = A.TrackConfig(fps=fps, bank=A.BankConfig.from_notes(15, 129, piano=True))
+    want = A.audio_track(clip, frames, cfg)
+    assert np.array_equal(want["tell"], tell) and np.array_equal(want["dt"], dt)
+    seen = []
+    scene = streamed_visualizer(clip, tell, seen)
+    scene.initialize()
+    scene.cuda = OracleContext()
+    scene.main(width=64, height=36, time=seconds, fps=fps, output=None, distributed=False)
+    assert len(seen) == frames and [s["tell"] for s in seen] == tell.tolist()
+    for k, s in enumerate(seen):
+        assert s["volume"] == want["volume"][k] and s["std"] == want["std"][k] and s["integral"] == want["volume_integral"][k]
+        assert np.array_equal(s["column"], want["column"][k]) and np.array_equal(s["wave"], want["wave"][k])
