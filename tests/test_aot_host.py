@@ -1,0 +1,134 @@
+"""The PRODUCTION per-fragment code on the CPU: the scene functions of csrc/scenes.cuh (with glsl.cuh and sampler.cuh —
+what screen_kernel / frame_kernel call for every fragment) compiled for the host with g++ over tests/aot_host_shim.h and
+run on the cases of oracle/glsl_cases.py against tests/golden/glsl_*.npz — the reference's shader text, executed.
+
+tests/test_gpu_golden.py makes the same comparison through the C ABI on the B200 (1e-3 per channel, north_star's gate);
+here, without a GPU and with libm instead of libdevice, the transliteration itself is held to the reference text much
+tighter: 1e-5 on the continuous scenes. -ffp-contract=off: one rounding per operation, as nvcc is told for these files
+(no FMA contraction differences are tolerated by the goldens' 1e-6 pin either).
+
+Covered here: the generic path of all 16 reference scenes (P.fast = 0). Not here: the variants that need tables the
+launcher builds in constant memory (scene_visualizer_fast's tap table) and the separable visualizer kernels
+(visualizer_rows.cu, visualizer_tiled.cuh) — those are held to this generic path and to the goldens on the device
+(tests/test_gpu_render.py, tests/test_gpu_golden.py)."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import glsl_cases as C
+from shaderflow_b200 import _native as N
+from tests.helpers import native_uniforms
+
+ROOT = Path(__file__).resolve().parents[1]
+CUDA_INCLUDE = Path("/usr/local/cuda/include")
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not (CUDA_INCLUDE/"cuda_runtime.h").exists(), reason="needs g++ and the CUDA headers")
+
+SOURCE = r'''
+#include "aot_host_shim.h"
+#include "sfb200.h"
+#include "render_params.h"
+#include "scenes.cuh"
+
+template <int SCENE> static void run(const RenderParams& P, FILE* out) {
+    for (int j = 0; j < P.Hr; j++)
+        for (int i = 0; i < P.Wr; i++) {
+            const glsl::vec4 c = glsl::shade<SCENE, false>(P, glsl::make_frag(P, i, j));
+            const float v[4] = {c.x, c.y, c.z, c.w};
+            fwrite(v, sizeof(float), 4, out);
+        }
+}
+
+int main(int argc, char** argv) {
+    static RenderParams P;
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(&P.u, sizeof(P.u), 1, f) != 1) return 2;
+    fclose(f);
+    const int scene = atoi(argv[2]);
+    P.Wr = atoi(argv[3]); P.Hr = atoi(argv[4]); P.W = int(P.u.iResolution[0]); P.H = int(P.u.iResolution[1]);
+    P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
+    P.fast = atoi(argv[6]);
+    for (int k = 0; 7 + 9*k < argc; k++) {                 // texture k: file w h padded comps dtype filter rx ry
+        char** a = argv + 7 + 9*k;
+        DevSampler& s = P.tex[k];
+        s.hw = 0; s.w = atoi(a[1]); s.h = atoi(a[2]); s.padded = atoi(a[3]); s.comps = atoi(a[4]); s.dtype = atoi(a[5]);
+        s.filter = atoi(a[6]); s.rx = atoi(a[7]); s.ry = atoi(a[8]);
+        const size_t bytes = size_t(s.w)*s.h*s.padded*(s.dtype == SFB_DTYPE_U8 ? 1 : 4);
+        void* data = malloc(bytes);
+        FILE* t = fopen(a[0], "rb");
+        if (!t || fread(data, 1, bytes, t) != bytes) return 3;
+        fclose(t);
+        s.lin = data;
+    }
+    FILE* out = fopen(argv[5], "wb");
+    switch (scene) {
+#define CASE(ID) case ID: run<ID>(P, out); break;
+        CASE(SFB_SCENE_DEFAULT) CASE(SFB_SCENE_SHADERTOY) CASE(SFB_SCENE_VISUALIZER) CASE(SFB_SCENE_BARS) CASE(SFB_SCENE_WAVEFORM)
+        CASE(SFB_SCENE_MANDELBROT) CASE(SFB_SCENE_TETRATION) CASE(SFB_SCENE_RAYMARCH) CASE(SFB_SCENE_MULTISHADER_CHILD)
+        CASE(SFB_SCENE_MULTISHADER) CASE(SFB_SCENE_MULTIPASS) CASE(SFB_SCENE_MOTIONBLUR) CASE(SFB_SCENE_DYNAMICS) CASE(SFB_SCENE_AUDIO)
+        CASE(SFB_SCENE_LIFE_SIMULATION) CASE(SFB_SCENE_LIFE_VISUALS) CASE(SFB_SCENE_PIANO)
+        default: return 4;
+    }
+    fclose(out);
+    return 0;
+}
+'''
+
+CASES = {c.name: c for c in C.small_cases()}
+# continuous scenes are held everywhere; the others branch on thresholds and may flip a fragment on an ulp
+CONTINUOUS = {"default", "default_stereo", "default_equirect", "default_rotated", "shadertoy", "dynamics", "audio",
+              "multishader_child", "multishader", "multipass_layer0", "multipass_layer1", "motionblur_layer0", "motionblur_layer1"}
+
+
+@pytest.fixture(scope="module")
+def binary(tmp_path_factory):
+    work = tmp_path_factory.mktemp("aot")
+    (work/"scenes_host.cpp").write_text(SOURCE)
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-I", str(ROOT/"tests"), "-I", str(ROOT/"include"),
+                            "-I", str(CUDA_INCLUDE), "-I", str(ROOT/"shaderflow_b200"/"csrc"), str(work/"scenes_host.cpp"),
+                            "-o", str(work/"scenes_host")], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr[-3000:]
+    return work/"scenes_host"
+
+
+def run_scene(binary, tmp_path, case, fast: int = 0) -> np.ndarray:
+    sid = N.scene_lookup(case.scene)
+    info = N.scene_info(sid)
+    (tmp_path/"uniforms.bin").write_bytes(bytes(native_uniforms(case.uniforms, info)))
+    textures = case.tex                                                        # keyed like the scene's sampler table
+    args = []
+    for k, name in enumerate(info["samplers"]):
+        t = textures.get(name)
+        data = np.zeros((1, 1, 4), np.uint8) if t is None else t.data          # declared but never read by this pass
+        comps = data.shape[2]
+        if comps == 3:                                                         # stored padded to 4 components, alpha reads 1
+            data = np.concatenate([data, np.full(data.shape[:-1] + (1,), 255 if data.dtype == np.uint8 else 1.0, data.dtype)], -1)
+        (tmp_path/f"texture{k}.bin").write_bytes(np.ascontiguousarray(data).tobytes())
+        linear, rx, ry = (True, False, False) if t is None else (t.linear, t.repeat_x, t.repeat_y)
+        args += [str(tmp_path/f"texture{k}.bin"), data.shape[1], data.shape[0], data.shape[2], comps,
+                 N.DTYPE_U8 if data.dtype == np.uint8 else N.DTYPE_F32, int(linear), int(rx), int(ry)]
+    done = subprocess.run([str(binary), str(tmp_path/"uniforms.bin"), str(sid), str(case.Wr), str(case.Hr), str(tmp_path/"out.bin"), str(fast),
+                           *map(str, args)], capture_output=True, text=True)
+    assert done.returncode == 0, (done.returncode, done.stderr[-500:])
+    return np.fromfile(tmp_path/"out.bin", np.float32).reshape(case.Hr, case.Wr, 4)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_production_scene_functions_reproduce_the_reference_text(binary, tmp_path, golden_dir, name):
+    case = CASES[name]
+    want = np.load(golden_dir/f"glsl_{name}.npz")["screen_f32"]
+    got = run_scene(binary, tmp_path, case)
+    if case.rows is not None:
+        got = got[case.rows]
+    if case.scene == "life_simulation":
+        got, want = got[..., :1], want[..., :1]                                # the program writes .r (a one-component target)
+    error = np.abs(got - want)/np.maximum(1.0, np.abs(want))
+    error = np.nan_to_num(error, nan=0.0)
+    if name in CONTINUOUS:
+        assert error.max() <= 5e-5, (name, float(error.max()))                 # (asin / atan of the equirectangular camera: 1.7e-5)
+    else:
+        least = 0.98 if case.scene == "tetration" else 0.995                   # 67 complex powers amplify an ulp of pow / exp
+        assert (error <= 1e-5).mean() >= least, (name, float((error <= 1e-5).mean()), float(error.max()))
+    assert np.median(error) <= 1e-6
