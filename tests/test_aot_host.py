@@ -33,12 +33,19 @@ SOURCE = r'''
 #include "scenes.cuh"
 
 template <int SCENE> static void run(const RenderParams& P, FILE* out) {
-    for (int j = 0; j < P.Hr; j++)
+    const char* rows = getenv("SFB_ROWS");                  // "j0,j1,…": only these fragment rows (the 4K bands)
+    for (int j = 0; j < P.Hr; j++) {
+        if (rows) {
+            bool wanted = false;
+            for (const char* p = rows; *p; ) { if (atoi(p) == j) wanted = true; while (*p && *p != ',') p++; if (*p) p++; }
+            if (!wanted) continue;
+        }
         for (int i = 0; i < P.Wr; i++) {
             const glsl::vec4 c = glsl::shade<SCENE, false>(P, glsl::make_frag(P, i, j));
             const float v[4] = {c.x, c.y, c.z, c.w};
             fwrite(v, sizeof(float), 4, out);
         }
+    }
 }
 
 int main(int argc, char** argv) {
@@ -93,7 +100,7 @@ def binary(tmp_path_factory):
     return work/"scenes_host"
 
 
-def run_scene(binary, tmp_path, case, fast: int = 0) -> np.ndarray:
+def run_scene(binary, tmp_path, case, fast: int = 0, rows=None) -> np.ndarray:
     sid = N.scene_lookup(case.scene)
     info = N.scene_info(sid)
     (tmp_path/"uniforms.bin").write_bytes(bytes(native_uniforms(case.uniforms, info)))
@@ -109,10 +116,14 @@ def run_scene(binary, tmp_path, case, fast: int = 0) -> np.ndarray:
         linear, rx, ry = (True, False, False) if t is None else (t.linear, t.repeat_x, t.repeat_y)
         args += [str(tmp_path/f"texture{k}.bin"), data.shape[1], data.shape[0], data.shape[2], comps,
                  N.DTYPE_U8 if data.dtype == np.uint8 else N.DTYPE_F32, int(linear), int(rx), int(ry)]
+    import os
+    env = dict(os.environ)
+    if rows is not None:
+        env["SFB_ROWS"] = ",".join(str(int(r)) for r in rows)
     done = subprocess.run([str(binary), str(tmp_path/"uniforms.bin"), str(sid), str(case.Wr), str(case.Hr), str(tmp_path/"out.bin"), str(fast),
-                           *map(str, args)], capture_output=True, text=True)
+                           *map(str, args)], capture_output=True, text=True, env=env)
     assert done.returncode == 0, (done.returncode, done.stderr[-500:])
-    return np.fromfile(tmp_path/"out.bin", np.float32).reshape(case.Hr, case.Wr, 4)
+    return np.fromfile(tmp_path/"out.bin", np.float32).reshape(case.Hr if rows is None else len(rows), case.Wr, 4)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -131,4 +142,17 @@ def test_production_scene_functions_reproduce_the_reference_text(binary, tmp_pat
     else:
         least = 0.98 if case.scene == "tetration" else 0.995                   # 67 complex powers amplify an ulp of pow / exp
         assert (error <= 1e-5).mean() >= least, (name, float((error <= 1e-5).mean()), float(error.max()))
+    assert np.median(error) <= 1e-6
+
+
+def test_generic_visualizer_at_the_benchmarked_geometry(binary, tmp_path, golden_dir):
+    """BASELINE configs[2]: 3840 x 2160, ssaa 2 → a 7680 x 4320 target over the 1920 x 1080 background. Four 8-row bands
+    of it (the golden's), every fragment of those rows, through the generic visualizer scene function on the host"""
+    case = C.band_case()
+    gold = np.load(golden_dir/"glsl_visualizer_4k_bands.npz")
+    want = gold["screen_f32"]
+    got = run_scene(binary, tmp_path, case, rows=case.rows)
+    got = got if case.cols is None else got[:, case.cols]
+    error = np.abs(got - want)/np.maximum(1.0, np.abs(want))
+    assert (error <= 1e-5).mean() >= 0.999, (float((error <= 1e-5).mean()), float(error.max()))
     assert np.median(error) <= 1e-6
