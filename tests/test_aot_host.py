@@ -7,7 +7,8 @@ here, without a GPU and with libm instead of libdevice, the transliteration itse
 tighter: 1e-5 on the continuous scenes. -ffp-contract=off: one rounding per operation, as nvcc is told for these files
 (no FMA contraction differences are tolerated by the goldens' 1e-6 pin either).
 
-Covered here: the generic path of all 16 reference scenes (P.fast = 0). Not here: the variants that need tables the
+Covered here: the generic path of all 16 reference scenes (P.fast = 0), the default fast variants of the two fractals, and
+the generic visualizer on four bands of the benchmarked 4K geometry. Not here: the variants that need tables the
 launcher builds in constant memory (scene_visualizer_fast's tap table) and the separable visualizer kernels
 (visualizer_rows.cu, visualizer_tiled.cuh) — those are held to this generic path and to the goldens on the device
 (tests/test_gpu_render.py, tests/test_gpu_golden.py)."""
@@ -156,3 +157,18 @@ def test_generic_visualizer_at_the_benchmarked_geometry(binary, tmp_path, golden
     error = np.abs(got - want)/np.maximum(1.0, np.abs(want))
     assert (error <= 1e-5).mean() >= 0.999, (float((error <= 1e-5).mean()), float(error.max()))
     assert np.median(error) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["mandelbrot", "tetration"])
+def test_default_fast_variants_of_the_fractals(binary, tmp_path, golden_dir, name):
+    """What the launcher runs by default for the two fractals (render.cu: P.fast = 1 unless SFB_RENDER_LITERAL — the
+    closed-form interior tests of the Mandelbrot set, one exp of the combined exponent per tetration step): the
+    variants BASELINE configs[3] is measured with, against the reference text's goldens"""
+    case = CASES[name]
+    want = np.load(golden_dir/f"glsl_{name}.npz")["screen_f32"]
+    literal, fast = run_scene(binary, tmp_path, case, fast=0), run_scene(binary, tmp_path, case, fast=1)
+    for got, least in ((fast, 0.97 if name == "tetration" else 0.995),):
+        error = np.abs(got - want)/np.maximum(1.0, np.abs(want))
+        assert (error <= 1e-4).mean() >= least, (name, float((error <= 1e-4).mean()), float(error.max()))
+        assert np.median(error) <= 1e-6
+    assert (np.abs(fast - literal) <= 1e-4).mean() >= (0.97 if name == "tetration" else 0.999)
