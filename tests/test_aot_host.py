@@ -8,9 +8,10 @@ tighter: 1e-5 on the continuous scenes. -ffp-contract=off: one rounding per oper
 (no FMA contraction differences are tolerated by the goldens' 1e-6 pin either).
 
 Covered here: the generic path of all 16 reference scenes (P.fast = 0), the default fast variants of the two fractals, and
-the generic visualizer on four bands of the benchmarked 4K geometry. Not here: the variants that need tables the
-launcher builds in constant memory (scene_visualizer_fast's tap table) and the separable visualizer kernels
-(visualizer_rows.cu, visualizer_tiled.cuh) — those are held to this generic path and to the goldens on the device
+the generic visualizer on four bands of the benchmarked 4K geometry. Also the table-driven visualizer
+(scene_visualizer_fast; its constant-memory tap table is filled by the harness with the launcher's float loops). Not
+here: the separable visualizer kernels (visualizer_rows.cu, visualizer_tiled.cuh) — those are held to this generic
+path and to the goldens on the device
 (tests/test_gpu_render.py, tests/test_gpu_golden.py)."""
 import shutil
 import subprocess
@@ -69,6 +70,17 @@ int main(int argc, char** argv) {
         if (!t || fread(data, 1, bytes, t) != bytes) return 3;
         fclose(t);
         s.lin = data;
+    }
+    {   // the tap table the launcher keeps in constant memory (render_kernels.cuh build_blur_table), same float loops
+        const volatile float TAU_F = 6.2831853071795864f, directions = 8.0f, quality = 10.0f;
+        int n = 0;
+        for (volatile float angle = 0.0f; angle < TAU_F; angle = angle + TAU_F/directions) {
+            const float c = cosf(angle), s = sinf(angle);
+            for (volatile float walk = 1.0f/quality; walk <= 1.001f; walk = walk + 1.0f/quality)
+                if (n < 90) glsl::c_blur.tap[n++] = make_float2(c*walk, s*walk);
+        }
+        if (n != 90) return 5;
+        glsl::c_blur.tap[90] = glsl::c_blur.tap[91] = make_float2(0.0f, 0.0f);
     }
     FILE* out = fopen(argv[5], "wb");
     switch (scene) {
@@ -172,3 +184,15 @@ def test_default_fast_variants_of_the_fractals(binary, tmp_path, golden_dir, nam
         assert (error <= 1e-4).mean() >= least, (name, float((error <= 1e-4).mean()), float(error.max()))
         assert np.median(error) <= 1e-6
     assert (np.abs(fast - literal) <= 1e-4).mean() >= (0.97 if name == "tetration" else 0.999)
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c.scene == "visualizer"])
+def test_visualizer_table_driven_path_reproduces_the_reference_text(binary, tmp_path, golden_dir, name):
+    """scene_visualizer_fast — the hoisted tap table, texel arithmetic in byte units, the quad cache: what the
+    one-thread-per-fragment kernels run by default for the Visualizer — against the same goldens and the literal path"""
+    case = CASES[name]
+    want = np.load(golden_dir/f"glsl_{name}.npz")["screen_f32"]
+    literal, fast = run_scene(binary, tmp_path, case, fast=0), run_scene(binary, tmp_path, case, fast=1)
+    error = np.abs(fast - want)/np.maximum(1.0, np.abs(want))
+    assert (error <= 1e-5).mean() >= 0.995, (name, float((error <= 1e-5).mean()), float(error.max()))
+    assert np.abs(fast - literal).max() <= 1e-5
