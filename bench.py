@@ -146,7 +146,18 @@ class ClockSampler:
 def cpu_sample(args) -> dict:
     from oracle import cpu_bench
     r = cpu_bench.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa, rows_per_band=8, bands_per_worker=3)
-    return dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+    out = dict(value=r["frames_per_s"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"])
+    try:                                                    # the compiled port beside the numpy one; the faster is the baseline
+        from oracle import cpu_compiled
+        c = cpu_compiled.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa)
+        out["numpy_port"] = dict(value=r["frames_per_s"], sample=r["sample"])
+        if c["frames_per_s"] > out["value"]:
+            out.update(value=c["frames_per_s"], cores=c["cores"], sample=c["sample"])
+        else:
+            out["compiled_port"] = dict(value=c["frames_per_s"], sample=c["sample"])
+    except Exception as error:
+        out["compiled_port"] = dict(error=str(error)[:200])
+    return out
 
 
 def run_reference(args, rank: int) -> None:
@@ -163,12 +174,23 @@ def run_reference(args, rank: int) -> None:
         if i >= args.warmup:
             values.append(last["frames_per_s"])
     value = float(np.mean(values)) if values else last["frames_per_s"]
+    ports = dict(numpy=dict(value=value, cores=last["cores"], sample=last["sample"]))
+    try:
+        # the same path as COMPILED code (csrc/scenes.cuh's generic visualizer function built for the host, oracle/cpu_compiled.py):
+        # llvmpipe would compile the GLSL to native code too, so the faster of the two ports is the line's value
+        from oracle import cpu_compiled
+        compiled = cpu_compiled.visualizer_sample(width=args.width, height=args.height, ssaa=args.ssaa)
+        ports["compiled"] = dict(value=compiled["frames_per_s"], cores=compiled["cores"], sample=compiled["sample"])
+        if compiled["frames_per_s"] > value:
+            value, last = compiled["frames_per_s"], dict(last, cores=compiled["cores"], sample=compiled["sample"])
+    except Exception as error:                              # no g++ / CUDA headers on the box: the numpy port stands alone
+        ports["compiled"] = dict(error=str(error)[:200])
     line = dict(impl="reference", metric=METRIC, value=value, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3/value, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", gpu_launches=0,
                 config=dict(workload=WORKLOAD, step="bounded sample of one frame: row bands shaded on every host core, extrapolated"),
                 cpu_baseline=dict(value=value, unit="frames/s", cores=last["cores"], kind="port", sample=last["sample"]),
-                e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), ports=ports)
     print(json.dumps(line), file=RESULT, flush=True)
 
 

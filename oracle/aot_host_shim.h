@@ -1,6 +1,6 @@
 // Host stand-ins for the few CUDA built-ins the ahead-of-time scene functions use (csrc/glsl.cuh, sampler.cuh, scenes.cuh),
 // so that the PRODUCTION per-fragment code — the functions screen_kernel / frame_kernel call — can be compiled with g++
-// and run on the CPU against the goldens (tests/test_aot_host.py). Test infrastructure only.
+// and run on the CPU against the goldens (tests/test_aot_host.py) and timed as a compiled CPU baseline (oracle/cpu_compiled.py). Test infrastructure only.
 #pragma once
 #include <cmath>
 #include <cstdint>

@@ -28,73 +28,8 @@ ROOT = Path(__file__).resolve().parents[1]
 CUDA_INCLUDE = Path("/usr/local/cuda/include")
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not (CUDA_INCLUDE/"cuda_runtime.h").exists(), reason="needs g++ and the CUDA headers")
 
-SOURCE = r'''
-#include "aot_host_shim.h"
-#include "sfb200.h"
-#include "render_params.h"
-#include "scenes.cuh"
+from oracle.cpu_compiled import SOURCE, SHIM_DIR      # the harness also times the compiled port for bench.py
 
-template <int SCENE> static void run(const RenderParams& P, FILE* out) {
-    const char* rows = getenv("SFB_ROWS");                  // "j0,j1,…": only these fragment rows (the 4K bands)
-    for (int j = 0; j < P.Hr; j++) {
-        if (rows) {
-            bool wanted = false;
-            for (const char* p = rows; *p; ) { if (atoi(p) == j) wanted = true; while (*p && *p != ',') p++; if (*p) p++; }
-            if (!wanted) continue;
-        }
-        for (int i = 0; i < P.Wr; i++) {
-            const glsl::vec4 c = glsl::shade<SCENE, false>(P, glsl::make_frag(P, i, j));
-            const float v[4] = {c.x, c.y, c.z, c.w};
-            fwrite(v, sizeof(float), 4, out);
-        }
-    }
-}
-
-int main(int argc, char** argv) {
-    static RenderParams P;
-    FILE* f = fopen(argv[1], "rb");
-    if (!f || fread(&P.u, sizeof(P.u), 1, f) != 1) return 2;
-    fclose(f);
-    const int scene = atoi(argv[2]);
-    P.Wr = atoi(argv[3]); P.Hr = atoi(argv[4]); P.W = int(P.u.iResolution[0]); P.H = int(P.u.iResolution[1]);
-    P.inv_Wr = 1.0/double(P.Wr); P.inv_Hr = 1.0/double(P.Hr);
-    P.fast = atoi(argv[6]);
-    for (int k = 0; 7 + 9*k < argc; k++) {                 // texture k: file w h padded comps dtype filter rx ry
-        char** a = argv + 7 + 9*k;
-        DevSampler& s = P.tex[k];
-        s.hw = 0; s.w = atoi(a[1]); s.h = atoi(a[2]); s.padded = atoi(a[3]); s.comps = atoi(a[4]); s.dtype = atoi(a[5]);
-        s.filter = atoi(a[6]); s.rx = atoi(a[7]); s.ry = atoi(a[8]);
-        const size_t bytes = size_t(s.w)*s.h*s.padded*(s.dtype == SFB_DTYPE_U8 ? 1 : 4);
-        void* data = malloc(bytes);
-        FILE* t = fopen(a[0], "rb");
-        if (!t || fread(data, 1, bytes, t) != bytes) return 3;
-        fclose(t);
-        s.lin = data;
-    }
-    {   // the tap table the launcher keeps in constant memory (render_kernels.cuh build_blur_table), same float loops
-        const volatile float TAU_F = 6.2831853071795864f, directions = 8.0f, quality = 10.0f;
-        int n = 0;
-        for (volatile float angle = 0.0f; angle < TAU_F; angle = angle + TAU_F/directions) {
-            const float c = cosf(angle), s = sinf(angle);
-            for (volatile float walk = 1.0f/quality; walk <= 1.001f; walk = walk + 1.0f/quality)
-                if (n < 90) glsl::c_blur.tap[n++] = make_float2(c*walk, s*walk);
-        }
-        if (n != 90) return 5;
-        glsl::c_blur.tap[90] = glsl::c_blur.tap[91] = make_float2(0.0f, 0.0f);
-    }
-    FILE* out = fopen(argv[5], "wb");
-    switch (scene) {
-#define CASE(ID) case ID: run<ID>(P, out); break;
-        CASE(SFB_SCENE_DEFAULT) CASE(SFB_SCENE_SHADERTOY) CASE(SFB_SCENE_VISUALIZER) CASE(SFB_SCENE_BARS) CASE(SFB_SCENE_WAVEFORM)
-        CASE(SFB_SCENE_MANDELBROT) CASE(SFB_SCENE_TETRATION) CASE(SFB_SCENE_RAYMARCH) CASE(SFB_SCENE_MULTISHADER_CHILD)
-        CASE(SFB_SCENE_MULTISHADER) CASE(SFB_SCENE_MULTIPASS) CASE(SFB_SCENE_MOTIONBLUR) CASE(SFB_SCENE_DYNAMICS) CASE(SFB_SCENE_AUDIO)
-        CASE(SFB_SCENE_LIFE_SIMULATION) CASE(SFB_SCENE_LIFE_VISUALS) CASE(SFB_SCENE_PIANO)
-        default: return 4;
-    }
-    fclose(out);
-    return 0;
-}
-'''
 
 CASES = {c.name: c for c in C.small_cases()}
 # continuous scenes are held everywhere; the others branch on thresholds and may flip a fragment on an ulp (SURVEY §7.5-2)
@@ -106,7 +41,7 @@ CONTINUOUS = {"default", "default_stereo", "default_equirect", "default_rotated"
 def binary(tmp_path_factory):
     work = tmp_path_factory.mktemp("aot")
     (work/"scenes_host.cpp").write_text(SOURCE)
-    build = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-I", str(ROOT/"tests"), "-I", str(ROOT/"include"),
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-I", str(SHIM_DIR), "-I", str(ROOT/"include"),
                             "-I", str(CUDA_INCLUDE), "-I", str(ROOT/"shaderflow_b200"/"csrc"), str(work/"scenes_host.cpp"),
                             "-o", str(work/"scenes_host")], capture_output=True, text=True)
     assert build.returncode == 0, build.stderr[-3000:]
